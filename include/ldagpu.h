@@ -1,0 +1,136 @@
+/*
+ * ldagpu.h -- C ABI of libldagpu.so, the B200-native Gibbs-sweep engine behind the reference's
+ * sampler interface (schemes "gpu_ggs" / "gpu_pcgs").
+ *
+ * The reference (clintpgeorge/LDAGroupedGibbsSampler, 100 % Java) has no native interface; the
+ * binding point is its sampler interface, so every entry point below names the Java method(s) it
+ * serves.  Paths are relative to src/main/java/cc/mallet/ of the reference:
+ *   LGS  = topics/LDAGibbsSampler.java        (interface, :10-47)
+ *   LSWP = topics/LDASamplerWithPhi.java      (interface, :5-12)
+ *   UPL  = topics/UncollapsedParallelLDA.java
+ *   GGS  = topics/LDAGroupedGibbsSampler.java
+ *   PCGS = topics/LDAPartiallyCollapsedGibbsSampler.java
+ *   MSL  = topics/ModifiedSimpleLDA.java
+ *
+ * Conventions: every function returns 0 on success, non-zero on error (message through
+ * ldagpu_last_error).  The caller owns every buffer it passes; the library copies in/out and owns
+ * only device memory behind the opaque handle.  Matrices are flat row-major with the shape of the
+ * Java array they mirror.  One caller thread per handle; ldagpu_abort may be called from any
+ * thread.  There is no CPU fallback: without a CUDA device ldagpu_create fails.
+ */
+#ifndef LDAGPU_H
+#define LDAGPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ldagpu_handle_s *ldagpu_handle;
+
+#define LDAGPU_SCHEME_GGS 0  /* GGS:47-132, GGS:139-209 */
+#define LDAGPU_SCHEME_PCGS 1 /* UPL:1466-1545, PCGS:48-118 */
+
+/* version / build info ("libldagpu x.y sm_100a") */
+const char *ldagpu_version(void);
+/* message of the last failure on this handle (or of the last failed create when h == NULL) */
+const char *ldagpu_last_error(ldagpu_handle h);
+/* number of visible CUDA devices (0 if none / no driver) */
+int ldagpu_device_count(void);
+
+/*
+ * addInstances (LGS:13, UPL:357-456, GGS:33-37): upload one shard of the corpus in CSR form.
+ *   K, V           topics, vocabulary size
+ *   D, doc_offsets local documents and their int64[D+1] token offsets (doc_offsets[0] == 0)
+ *   tokens         int32[N] type ids, N = doc_offsets[D]
+ *   alpha          double[K]  (MSL:61-64), beta scalar
+ *   seed           Philox key of the in-sweep draws (the reference's are unseedable, UPL:1519, GGS:107)
+ *   scheme         LDAGPU_SCHEME_GGS | LDAGPU_SCHEME_PCGS   (factory switch, tui/ParallelLDA.java:401-490)
+ *   device         CUDA device ordinal
+ *   doc_base, token_base  global index of the shard's first document / token (0 on one GPU):
+ *                  random-number counters are keyed by global indices, so results do not depend
+ *                  on how the corpus is sharded
+ * The topic indicators start at 0; call ldagpu_init_z_java_random or ldagpu_set_z next.
+ */
+int ldagpu_create(int32_t K, int32_t V, int64_t D, const int64_t *doc_offsets, const int32_t *tokens,
+                  const double *alpha, double beta, uint64_t seed, int32_t scheme, int32_t device,
+                  int64_t doc_base, int64_t token_base, ldagpu_handle *out);
+int ldagpu_destroy(ldagpu_handle h);
+
+/* multi-GPU (one process per GPU).  Rank 0 makes an id, the host program broadcasts its 128 bytes
+ * (torch.distributed / any rendezvous), every rank joins.  After this, sweeps exchange counts with
+ * one reduce-scatter and Phi with one all-gather per sweep. */
+int ldagpu_comm_unique_id(void *id128);
+int ldagpu_comm_init(ldagpu_handle h, int32_t rank, int32_t world, const void *id128);
+
+/* initial z = MALLET Randoms(seed).nextInt(K) in document order (UPL:398-406,458-460; MSL:153-156).
+ * skip = number of draws consumed by the shards before this one (token_base on a sharded corpus).
+ * Rebuilds the counts and draws the initial Phi (UPL:450,1287-1294) with sweep counter 0. */
+int ldagpu_init_z_java_random(ldagpu_handle h, int32_t seed);
+/* setZIndicators (LGS:22, UPL:1797-1843): replace z, rebuild counts, redraw Phi (sweep counter
+ * unchanged).  redraw_phi = 0 keeps the current Phi (used by tests and by checkpoint restore). */
+int ldagpu_set_z(ldagpu_handle h, const int32_t *z, int32_t redraw_phi);
+/* getZIndicators (LGS:19, MSL:464-477) flattened in CSR order */
+int ldagpu_get_z(ldagpu_handle h, int32_t *z);
+
+/* sample(iterations) (LGS:15, UPL:552-943): n full sweeps = [theta] z, counts, Phi.
+ * Stops early when ldagpu_abort was called (UPL:645,906-910); *done receives the sweeps run. */
+int ldagpu_sweep(ldagpu_handle h, int32_t n, int32_t *done);
+/* sampleZGivenPhi(iterations) (LSWP:11, UPL:975-1014): z and counts only, Phi frozen */
+int ldagpu_sample_z_given_phi(ldagpu_handle h, int32_t n, int32_t *done);
+/* step-wise entry points (tests, and hosts that interleave their own hooks preZ/postZ/prePhi/postPhi,
+ * LGS:38-43, LSWP:9-10).  A full sweep is: next_iteration, [sample_theta], sample_z, rebuild_counts,
+ * sample_phi. */
+int ldagpu_next_iteration(ldagpu_handle h);
+int ldagpu_sample_theta(ldagpu_handle h);   /* GGS:60-72 */
+int ldagpu_sample_z(ldagpu_handle h);       /* GGS:79-130 / UPL:1491-1543 */
+int ldagpu_rebuild_counts(ldagpu_handle h); /* UPL:1107-1221 net effect (= UPL:1797-1830) */
+int ldagpu_sample_phi(ldagpu_handle h);     /* GGS:139-209 / PCGS:48-118 */
+int ldagpu_get_iteration(ldagpu_handle h, int32_t *it); /* getCurrentIteration (LGS:18) */
+int ldagpu_set_iteration(ldagpu_handle h, int32_t it);
+
+/* getTypeTopicMatrix / getTypeTopicCounts (LGS:32, UPL:226-234): int32[V][K] (collective when sharded) */
+int ldagpu_get_type_topic_counts(ldagpu_handle h, int32_t *n_wk);
+/* getTopicTotals (LGS:33, MSL:971-976): int32[K] */
+int ldagpu_get_topic_totals(ldagpu_handle h, int32_t *n_k);
+/* getDocumentTopicMatrix (LGS:31, MSL:536-547): int32[D][K] for the local documents */
+int ldagpu_get_doc_topic_counts(ldagpu_handle h, int32_t *n_dk);
+/* getPhi (LSWP:6, UPL:1946-1948): double[K][V];  setPhi (LSWP:7, UPL:1897-1926) */
+int ldagpu_get_phi(ldagpu_handle h, double *phi);
+int ldagpu_set_phi(ldagpu_handle h, const double *phi);
+/* getPhiMeans (LSWP:8, UPL:1954-1966): double[K][V] = running sum / n_sampled; n_sampled = 0 means
+ * nothing accumulated yet (the Java side returns null).  Schedule: accumulate when
+ * iteration > burn_in && iteration % thin == 0 (UPL:1350-1352); burn_in <= 0 disables. */
+int ldagpu_set_phi_mean_schedule(ldagpu_handle h, int32_t burn_in, int32_t thin);
+int ldagpu_get_phi_mean(ldagpu_handle h, double *phi_mean, int32_t *n_sampled);
+/* GGS thetaMatrix (UPL:78, GGS:72): double[D][K] of the last sweep; set = test injection */
+int ldagpu_get_theta(ldagpu_handle h, double *theta);
+int ldagpu_set_theta(ldagpu_handle h, const double *theta);
+/* modelLogLikelihood (UPL:1644-1758) -> getLogLikelihood series is kept by the host (LGS:44) */
+int ldagpu_log_likelihood(ldagpu_handle h, double *ll);
+/* computeLogPosterior (UPL:1573-1634); GGS uses the sweep's theta (UPL:716-720) */
+int ldagpu_log_posterior(ldagpu_handle h, double *lp);
+
+/* abort()/getAbort() (topics/AbortableSampler.java:3-6, MSL:601-608); async-safe */
+int ldagpu_abort(ldagpu_handle h);
+int ldagpu_get_abort(ldagpu_handle h, int32_t *aborted);
+
+/* cumulative device time per phase in ms since creation (the reference's own timers:
+ * zSamplingTimeCum = z + count merge, phiSamplingTimeCum; UPL:642-644,670-673,690-693,931-939) */
+int ldagpu_get_timers(ldagpu_handle h, double *z_ms, double *counts_ms, double *phi_ms, double *comm_ms);
+/* device time of the dominant kernel (the z-step launches) over the last ldagpu_sweep /
+ * ldagpu_sample_z_given_phi call, and how many kernels that call launched */
+int ldagpu_get_last_call_stats(ldagpu_handle h, double *z_kernel_ms, int64_t *z_kernel_launches,
+                               int64_t *total_launches);
+
+/* host-side helper for benchmarks and tests: LDA-generative synthetic corpus of a given shape
+ * (SURVEY 8d).  doc_offsets int64[D+1] out; tokens int32[capacity] out; returns N in *n_tokens.
+ * Tokens of a document are sorted by type id (bag of words, like the bundled corpora). */
+int ldagpu_synth_corpus(int64_t D, int32_t V, int32_t K_gen, double mean_len, double sigma_len,
+                        int32_t max_len, uint64_t seed, int64_t *doc_offsets, int32_t *tokens,
+                        int64_t capacity, int64_t *n_tokens);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,144 @@
+// common.cuh -- shared declarations of the libldagpu kernels and their launchers.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ldagpu {
+
+constexpr int TILE = 128;            // topics per warp tile: lane l owns topics 4l..4l+3 of the tile
+constexpr int MAX_REG_TILES = 8;     // K <= 1024 keeps a whole Phi^T row in registers
+constexpr int GGS_CHUNK = 256;       // tokens per GGS work item (documents are split freely)
+constexpr int PHI_ROW_BLOCK = 8;     // words per sequential partial sum of the Phi normaliser
+constexpr int PHI_SEGMENTS = 8;      // vocabulary segments (= max ranks) of the Phi normaliser tree
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+struct Dims {
+    int32_t K;        // topics
+    int32_t Ks;       // row stride of Phi^T / n_wk / theta in elements: round_up(K, 32)
+    int32_t NT;       // tiles: ceil(K / 128)
+    int32_t V;        // vocabulary
+    int32_t Vp;       // padded vocabulary rows: round_up(V, 64)
+    int64_t D;        // local documents
+    int64_t N;        // local tokens
+    int64_t doc_base;    // global index of local document 0
+    int64_t token_base;  // global index of local token 0
+};
+
+struct ZArgs {
+    Dims dm;
+    const int64_t *doc_off;   // [D+1] local CSR
+    const int32_t *tokens;    // [N]
+    int32_t *z;               // [N] in/out
+    const float *phiT;        // [Vp][Ks]
+    const float *theta;       // [D][Ks] (GGS)
+    const float *alpha;       // [Ks]   (PCGS)
+    const int32_t *item_doc;  // GGS: [n_items] document of each chunk; PCGS: [D] LPT order
+    const int64_t *item_begin;// GGS: [n_items] first token of each chunk
+    int64_t n_items;
+    unsigned long long *work_counter;
+    uint32_t seed_lo, seed_hi, sweep;
+};
+
+struct ThetaArgs {
+    Dims dm;
+    const int64_t *doc_off;
+    const int32_t *z;
+    const float *alpha;   // [Ks]
+    float *theta;         // [D][Ks]
+    unsigned long long *work_counter;
+    uint32_t seed_lo, seed_hi, sweep;
+};
+
+// launchers (each returns the cudaError of the launch)
+cudaError_t launch_theta(const ThetaArgs &a, int sm_count, cudaStream_t st);
+cudaError_t launch_z_ggs(const ZArgs &a, int sm_count, cudaStream_t st);
+cudaError_t launch_z_pcgs(const ZArgs &a, int sm_count, cudaStream_t st);
+cudaError_t launch_counts(const Dims &dm, const int32_t *tokens, const int32_t *z, int32_t *n_wk,
+                          int32_t *n_k, int sm_count, cudaStream_t st);
+cudaError_t launch_topic_totals(const Dims &dm, const int32_t *n_wk, int32_t *n_k, cudaStream_t st);
+cudaError_t launch_doc_topic_counts(const Dims &dm, const int64_t *doc_off, const int32_t *z,
+                                    int32_t *n_dk /*[D][K] dense*/, cudaStream_t st);
+// Phi draw over rows [row0, row1) (multiples of 64); partial[(row/8)][Ks] fp64
+cudaError_t launch_phi_draw(const Dims &dm, const int32_t *n_wk, double beta, float *phiT,
+                            double *partial, int32_t row0, int32_t row1, uint32_t seed_lo,
+                            uint32_t seed_hi, uint32_t sweep, cudaStream_t st);
+// segment sums seg[s][Ks] for segments [seg0, seg1)
+cudaError_t launch_phi_segment_sums(const Dims &dm, const double *partial, double *seg, int seg0,
+                                    int seg1, cudaStream_t st);
+// S_k from the 8 segment sums, then normalise rows [row0,row1) and optionally add into phi_sum
+cudaError_t launch_phi_normalise(const Dims &dm, const double *seg, double *topic_sum, float *phiT,
+                                 double *phi_mean_sum, int32_t row0, int32_t row1, cudaStream_t st);
+// log-likelihood pieces: per-block partial sums (ll_type: pairs {sum, nnz})
+cudaError_t launch_ll_doc(const Dims &dm, const int64_t *doc_off, const int32_t *z,
+                          const double *alpha, double alpha_sum, double *partials, int n_partials,
+                          int sm_count, cudaStream_t st);
+cudaError_t launch_ll_type(const Dims &dm, const int32_t *n_wk, double beta, int32_t row0,
+                           int32_t row1, double *partials, int n_partials, cudaStream_t st);
+// log-posterior pieces (UncollapsedParallelLDA.java:1573-1634)
+cudaError_t launch_lp_tokens(const Dims &dm, const int32_t *tokens, const int32_t *z,
+                             const float *phiT, double *partials, int n_partials, cudaStream_t st);
+cudaError_t launch_lp_theta(const Dims &dm, const int64_t *doc_off, const int32_t *z,
+                            const float *theta, const double *alpha, double *partials,
+                            int n_partials, int sm_count, cudaStream_t st);
+cudaError_t launch_lp_phi(const Dims &dm, const float *phiT, double beta, int32_t row0, int32_t row1,
+                          double *partials, int n_partials, cudaStream_t st);
+// out[j] = sum_i partials[i*stride + j], sequential in i
+cudaError_t launch_sum_partials(const double *partials, int n, int stride, double *out, cudaStream_t st);
+
+// transposes / conversions for the accessors
+cudaError_t launch_export_phi(const Dims &dm, const float *phiT, double *phi_kv /*[K][V]*/, cudaStream_t st);
+cudaError_t launch_import_phi(const Dims &dm, const double *phi_kv, float *phiT, cudaStream_t st);
+cudaError_t launch_export_mean(const Dims &dm, const double *sum_vk, double scale, double *out_kv, cudaStream_t st);
+cudaError_t launch_export_counts(const Dims &dm, const int32_t *n_wk, int32_t *out_vk /*[V][K] dense*/, cudaStream_t st);
+cudaError_t launch_export_theta(const Dims &dm, const float *theta, double *out /*[D][K]*/, cudaStream_t st);
+cudaError_t launch_import_theta(const Dims &dm, const double *in, float *theta, cudaStream_t st);
+cudaError_t launch_validate(const Dims &dm, const int32_t *tokens, const int32_t *z, int *bad, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------
+// device helpers: mbarrier + 1-D bulk async copy (TMA engine, cp.async.bulk)
+// ---------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy, completion signalled on the mbarrier (bytes % 16 == 0, 16 B aligned)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+#endif
+
+}  // namespace ldagpu

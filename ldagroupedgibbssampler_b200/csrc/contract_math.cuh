@@ -1,0 +1,295 @@
+// contract_math.cuh -- device-side "contract" arithmetic of libldagpu.
+//
+// Everything is composed of IEEE-754 correctly rounded primitives in a fixed order
+// (explicit _rn intrinsics: nothing here may be re-associated or fused by the compiler),
+// so the CPU restatement in oracle/ reproduces the results bit for bit.  No libdevice
+// transcendental is used.
+//
+// Gamma sampler: Marsaglia-Tsang with the alpha<1 boost, as the reference states it in
+//   src/main/java/cc/mallet/util/ParallelRandoms.java:60-70 (rgamma), :148-159 (prgamma)
+// with its unseedable generators (ParallelRandoms.java:16-24,65,153-155) replaced by one
+// Philox4x32-10 block per attempt.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ldagpu {
+
+enum : uint32_t { STREAM_Z = 1, STREAM_THETA = 2, STREAM_PHI = 3 };
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based generator
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0;
+        uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// open-interval uniform from the top 23 bits: (n + 1/2) 2^-23, exact in fp32
+__device__ __forceinline__ float uniform23(uint32_t w)
+{
+    return __fmul_rn(__fadd_rn(__uint2float_rn(w >> 9), 0.5f), 0x1p-23f);
+}
+
+// ---------------------------------------------------------------------------------------
+// per-type primitives
+// ---------------------------------------------------------------------------------------
+template <typename T> struct CM;
+
+template <> struct CM<float> {
+    using real = float;
+    using U = uint32_t;
+    using S = int32_t;
+    static constexpr int MANT = 23, BIAS = 127, LN_TERMS = 5, EXP_DEG = 7, TRIG_DEG = 5, DENORM_SHIFT = 23;
+    static constexpr U SQRT_HALF = 0x3f3504f3u, MANT_MASK = 0x007fffffu, MIN_NORMAL = 0x00800000u;
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+    static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+    static __device__ __forceinline__ float rint(float a) { return rintf(a); }
+    static __device__ __forceinline__ U bits(float a) { return __float_as_uint(a); }
+    static __device__ __forceinline__ float from(U a) { return __uint_as_float(a); }
+    static __device__ __forceinline__ float from_int(S a) { return __int2float_rn(a); }
+    static __device__ __forceinline__ S to_int(float a) { return __float2int_rn(a); }
+    static __device__ __forceinline__ float denorm_scale() { return 0x1p23f; }
+    static __device__ __forceinline__ float exp_cutoff() { return -104.0f; }
+    static __device__ __forceinline__ float ln2_hi() { return 0x1.62ep-1f; }
+    static __device__ __forceinline__ float ln2_lo() { return 0x1.0bfbe8p-15f; }
+    static __device__ __forceinline__ float uni(uint32_t w) { return uniform23(w); }
+    static __device__ __forceinline__ float ang_frac(uint32_t w, bool odd)
+    {
+        uint32_t b = ((w >> 6) & 0x7fffffu) ^ (odd ? 0x7fffffu : 0u);
+        return __fmul_rn(__fadd_rn(__uint2float_rn(b), 0.5f), 0x1p-23f);
+    }
+};
+
+template <> struct CM<double> {
+    using real = double;
+    using U = unsigned long long;
+    using S = long long;
+    static constexpr int MANT = 52, BIAS = 1023, LN_TERMS = 11, EXP_DEG = 14, TRIG_DEG = 9, DENORM_SHIFT = 54;
+    static constexpr U SQRT_HALF = 0x3fe6a09e667f3bcdull, MANT_MASK = 0x000fffffffffffffull,
+                       MIN_NORMAL = 0x0010000000000000ull;
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+    static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
+    static __device__ __forceinline__ double rint(double a) { return ::rint(a); }
+    static __device__ __forceinline__ U bits(double a) { return (U)__double_as_longlong(a); }
+    static __device__ __forceinline__ double from(U a) { return __longlong_as_double((long long)a); }
+    static __device__ __forceinline__ double from_int(S a) { return __ll2double_rn(a); }
+    static __device__ __forceinline__ S to_int(double a) { return __double2ll_rn(a); }
+    static __device__ __forceinline__ double denorm_scale() { return 0x1p54; }
+    static __device__ __forceinline__ double exp_cutoff() { return -746.0; }
+    static __device__ __forceinline__ double ln2_hi() { return 0x1.62e42feep-1; }
+    static __device__ __forceinline__ double ln2_lo() { return 0x1.a39ef35793c76p-33; }
+    static __device__ __forceinline__ double uni(uint32_t w)
+    {
+        return __dmul_rn(__dadd_rn(__uint2double_rn(w), 0.5), 0x1p-32);
+    }
+    static __device__ __forceinline__ double ang_frac(uint32_t w, bool odd)
+    {
+        uint32_t b = (w & 0x1fffffffu) ^ (odd ? 0x1fffffffu : 0u);
+        return __dmul_rn(__dadd_rn(__uint2double_rn(b), 0.5), 0x1p-29);
+    }
+};
+
+// 1/(2n+1)
+template <typename T> __device__ __forceinline__ T coef_odd(int n)
+{
+    switch (n) {
+    case 0: return T(1.0);
+    case 1: return T(1.0 / 3.0);
+    case 2: return T(1.0 / 5.0);
+    case 3: return T(1.0 / 7.0);
+    case 4: return T(1.0 / 9.0);
+    case 5: return T(1.0 / 11.0);
+    case 6: return T(1.0 / 13.0);
+    case 7: return T(1.0 / 15.0);
+    case 8: return T(1.0 / 17.0);
+    case 9: return T(1.0 / 19.0);
+    default: return T(1.0 / 21.0);
+    }
+}
+// 1/n!
+template <typename T> __device__ __forceinline__ T coef_invfact(int n)
+{
+    switch (n) {
+    case 0: return T(1.0);
+    case 1: return T(1.0);
+    case 2: return T(1.0 / 2.0);
+    case 3: return T(1.0 / 6.0);
+    case 4: return T(1.0 / 24.0);
+    case 5: return T(1.0 / 120.0);
+    case 6: return T(1.0 / 720.0);
+    case 7: return T(1.0 / 5040.0);
+    case 8: return T(1.0 / 40320.0);
+    case 9: return T(1.0 / 362880.0);
+    case 10: return T(1.0 / 3628800.0);
+    case 11: return T(1.0 / 39916800.0);
+    case 12: return T(1.0 / 479001600.0);
+    case 13: return T(1.0 / 6227020800.0);
+    default: return T(1.0 / 87178291200.0);
+    }
+}
+// (-1)^n/(2n+1)!
+template <typename T> __device__ __forceinline__ T coef_sin(int n)
+{
+    switch (n) {
+    case 0: return T(1.0);
+    case 1: return T(-1.0 / 6.0);
+    case 2: return T(1.0 / 120.0);
+    case 3: return T(-1.0 / 5040.0);
+    case 4: return T(1.0 / 362880.0);
+    case 5: return T(-1.0 / 39916800.0);
+    case 6: return T(1.0 / 6227020800.0);
+    case 7: return T(-1.0 / 1307674368000.0);
+    case 8: return T(1.0 / 355687428096000.0);
+    default: return T(-1.0 / 121645100408832000.0);
+    }
+}
+// (-1)^n/(2n)!
+template <typename T> __device__ __forceinline__ T coef_cos(int n)
+{
+    switch (n) {
+    case 0: return T(1.0);
+    case 1: return T(-1.0 / 2.0);
+    case 2: return T(1.0 / 24.0);
+    case 3: return T(-1.0 / 720.0);
+    case 4: return T(1.0 / 40320.0);
+    case 5: return T(-1.0 / 3628800.0);
+    case 6: return T(1.0 / 479001600.0);
+    case 7: return T(-1.0 / 87178291200.0);
+    case 8: return T(1.0 / 20922789888000.0);
+    default: return T(-1.0 / 6402373705728000.0);
+    }
+}
+
+// natural logarithm, x > 0 finite
+template <typename T> __device__ __forceinline__ T c_ln(T x)
+{
+    using M = CM<T>;
+    typename M::U ix = M::bits(x);
+    typename M::S e = 0;
+    if (ix < M::MIN_NORMAL) {
+        x = M::mul(x, M::denorm_scale());
+        ix = M::bits(x);
+        e = -(typename M::S)M::DENORM_SHIFT;
+    }
+    typename M::U t = ix - M::SQRT_HALF;
+    e += (typename M::S)t >> M::MANT;
+    T m = M::from((t & M::MANT_MASK) + M::SQRT_HALF);
+    T s = M::div(M::sub(m, T(1.0)), M::add(m, T(1.0)));
+    T s2 = M::mul(s, s);
+    T p = coef_odd<T>(M::LN_TERMS - 1);
+#pragma unroll
+    for (int n = M::LN_TERMS - 2; n >= 0; --n) p = M::fma(p, s2, coef_odd<T>(n));
+    T lnm = M::mul(M::mul(T(2.0), s), p);
+    return M::fma(M::from_int(e), T(0.693147180559945309417232121458), lnm);
+}
+
+// exponential for y <= 0
+template <typename T> __device__ __forceinline__ T c_exp_neg(T y)
+{
+    using M = CM<T>;
+    if (y < M::exp_cutoff()) return T(0.0);
+    T n = M::rint(M::mul(y, T(1.44269504088896340735992468100)));
+    T r = M::fma(-n, M::ln2_hi(), y);
+    r = M::fma(-n, M::ln2_lo(), r);
+    T p = coef_invfact<T>(M::EXP_DEG);
+#pragma unroll
+    for (int k = M::EXP_DEG - 1; k >= 0; --k) p = M::fma(p, r, coef_invfact<T>(k));
+    typename M::S ni = M::to_int(n);
+    typename M::S n1 = ni >> 1;
+    typename M::S n2 = ni - n1;
+    T s1 = M::from((typename M::U)(n1 + M::BIAS) << M::MANT);
+    T s2 = M::from((typename M::U)(n2 + M::BIAS) << M::MANT);
+    return M::mul(M::mul(p, s1), s2);
+}
+
+// cos(2 pi t), t given by a 32-bit word: octant (3 bits) + fraction
+template <typename T> __device__ __forceinline__ T c_cos2pi(uint32_t w)
+{
+    using M = CM<T>;
+    uint32_t o = w >> 29;
+    bool odd = (o & 1u) != 0;
+    bool use_sin = (((o + 1u) >> 1) & 1u) != 0;
+    bool neg = (o >= 2u && o <= 5u);
+    T f = M::ang_frac(w, odd);
+    T a = M::mul(f, T(0.785398163397448309615660845820));
+    T a2 = M::mul(a, a);
+    T p = use_sin ? coef_sin<T>(M::TRIG_DEG) : coef_cos<T>(M::TRIG_DEG);
+#pragma unroll
+    for (int k = M::TRIG_DEG - 1; k >= 0; --k)
+        p = M::fma(p, a2, use_sin ? coef_sin<T>(k) : coef_cos<T>(k));
+    if (use_sin) p = M::mul(p, a);
+    return neg ? -p : p;
+}
+
+// One Marsaglia-Tsang attempt.  Returns true and sets g on acceptance.
+// d, c are the per-cell constants (d = aa - 1/3, c = 1/sqrt(9 d)); inv-boost shape a (< 1) if boost.
+template <typename T>
+__device__ __forceinline__ bool gamma_attempt(T a, bool boost, T d, T c, uint4 w, T &g)
+{
+    using M = CM<T>;
+    T u1 = M::uni(w.x);
+    T x = M::mul(M::sqrt(M::mul(T(-2.0), c_ln<T>(u1))), c_cos2pi<T>(w.y));
+    T v = M::fma(c, x, T(1.0));
+    if (!(v > T(0.0))) return false;
+    v = M::mul(M::mul(v, v), v);
+    T x2 = M::mul(x, x);
+    T x4 = M::mul(x2, x2);
+    T u = M::uni(w.z);
+    bool accept = u < M::fma(T(-0.0331), x4, T(1.0));
+    if (!accept) {
+        T t = M::add(M::sub(T(1.0), v), c_ln<T>(v));
+        accept = c_ln<T>(u) < M::fma(T(0.5), x2, M::mul(d, t));
+    }
+    if (!accept) return false;
+    g = M::mul(d, v);
+    if (boost) {
+        T ub = M::uni(w.w);
+        g = M::mul(g, c_exp_neg<T>(M::div(c_ln<T>(ub), a)));
+    }
+    return true;
+}
+
+template <typename T> __device__ __forceinline__ void gamma_setup(T a, bool &boost, T &d, T &c)
+{
+    using M = CM<T>;
+    boost = a < T(1.0);
+    T aa = boost ? M::add(a, T(1.0)) : a;
+    d = M::sub(aa, T(1.0 / 3.0));
+    c = M::div(T(1.0), M::sqrt(M::mul(T(9.0), d)));
+}
+
+// Complete draw for one cell (loops over attempts).
+template <typename T>
+__device__ __forceinline__ T c_gamma(T a, uint32_t k0, uint32_t k1, unsigned long long cell,
+                                     uint32_t sweep, uint32_t stream)
+{
+    bool boost;
+    T d, c, g = T(0.0);
+    gamma_setup<T>(a, boost, d, c);
+    for (uint32_t attempt = 0;; ++attempt) {
+        uint4 w = philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), sweep, (stream << 24) | attempt, k0, k1);
+        if (gamma_attempt<T>(a, boost, d, c, w, g)) return g;
+    }
+}
+
+}  // namespace ldagpu

@@ -1,0 +1,810 @@
+// engine.cu -- host side of libldagpu.so: the handle, the sweep driver, the NCCL exchange step and
+// the C ABI declared in include/ldagpu.h.
+//
+// One sweep (reference order: topics/UncollapsedParallelLDA.java:645-693):
+//   [GGS] theta_kernel        theta_d ~ Dir(n_d + alpha)                 (GGS:60-72)
+//   z_kernel                  z_i | theta/n_d, Phi                        (GGS:79-130, UPL:1491-1543)
+//   counts_kernel             n_wk, n_k from z                            (UPL:1107-1221 net effect)
+//   [G>1] reduce-scatter n_wk by vocabulary slice, all-reduce n_k         (stand-in for the shared
+//                                                                         AtomicInteger[K][V], UPL:102)
+//   phi_draw / segments       Gamma(beta + n_wk) for the rank's slice     (GGS:182-192, PCGS:91-101)
+//   [G>1] all-gather the 8 segment sums
+//   phi_normalise             rows of the slice
+//   [G>1] all-gather Phi^T
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/ldagpu.h"
+#include "common.cuh"
+
+using namespace ldagpu;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ---- NCCL through dlopen: single-GPU users need no NCCL at all -----------------------------
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*ReduceScatter)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string err;
+    bool load()
+    {
+        if (lib) return true;
+        // resolves to the copy already mapped into the process (torch's bundled NCCL) when there is one
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) { err = std::string("dlopen libnccl.so.2: ") + dlerror(); return false; }
+#define LD(field, sym)                                                          \
+    field = reinterpret_cast<decltype(field)>(dlsym(lib, sym));                 \
+    if (!field) { err = std::string("dlsym ") + sym + " failed"; lib = nullptr; return false; }
+        LD(GetUniqueId, "ncclGetUniqueId")
+        LD(CommInitRank, "ncclCommInitRank")
+        LD(CommDestroy, "ncclCommDestroy")
+        LD(ReduceScatter, "ncclReduceScatter")
+        LD(AllGather, "ncclAllGather")
+        LD(AllReduce, "ncclAllReduce")
+        LD(GetErrorString, "ncclGetErrorString")
+#undef LD
+        return true;
+    }
+};
+NcclApi g_nccl;
+
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count)
+    {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc(reinterpret_cast<void **>(&p), sizeof(T) * count);
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+// java.util.Random, JDK 8 specification (the reference's initial z: UPL:398-406,458-460)
+struct JavaRandom {
+    uint64_t s;
+    explicit JavaRandom(int64_t seed) : s(((uint64_t)seed ^ 0x5DEECE66Dull) & ((1ull << 48) - 1)) {}
+    int32_t next(int bits)
+    {
+        s = (s * 0x5DEECE66Dull + 0xBull) & ((1ull << 48) - 1);
+        return (int32_t)(uint32_t)(s >> (48 - bits));
+    }
+    int32_t nextInt(int32_t bound)
+    {
+        int32_t r = next(31);
+        int32_t m = bound - 1;
+        if ((bound & m) == 0) return (int32_t)(((int64_t)bound * (int64_t)r) >> 31);
+        for (int32_t u = r;; u = next(31)) {
+            r = u % bound;
+            if ((int32_t)((uint32_t)u - (uint32_t)r + (uint32_t)m) >= 0) break;
+        }
+        return r;
+    }
+};
+
+constexpr int N_PARTIALS = 592;   // 4 CTAs per SM on a 148-SM part; fixed so sums are reproducible
+constexpr int EV_PER_SWEEP = 9;
+
+}  // namespace
+
+struct ldagpu_handle_s {
+    Dims dm{};
+    int scheme = 0, device = 0, sm_count = 148;
+    double beta = 0.0, alpha_sum = 0.0;
+    std::vector<double> alpha;
+    uint64_t seed = 0;
+    int32_t iteration = 0;
+    int64_t D_global = 0;
+
+    DevBuf<int64_t> doc_off, item_begin;
+    DevBuf<int32_t> tokens, z, n_wk, n_k, item_doc, scratch_i32;
+    DevBuf<float> phiT, theta, alpha_f;
+    DevBuf<double> alpha_d, partial, seg, topic_sum, phi_mean, red, red_out, scratch_f64;
+    DevBuf<unsigned long long> counter;
+    DevBuf<int> bad;
+    int64_t n_items = 0;
+    std::vector<int64_t> h_doc_off;
+
+    int32_t mean_burn_in = 0, mean_thin = 1, n_sampled_phi = 0;
+
+    cudaStream_t stream = nullptr;
+    std::vector<cudaEvent_t> events;
+
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    int32_t row0 = 0, row1 = 0, seg0 = 0, seg1 = PHI_SEGMENTS;
+
+    std::atomic<int> abort_flag{0};
+    std::string err;
+    double t_z = 0, t_counts = 0, t_phi = 0, t_comm = 0;
+    double last_zk_ms = 0;
+    int64_t last_zk_launches = 0, last_launches = 0;
+
+    int fail(const char *fmt, ...)
+    {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return 1;
+    }
+};
+
+#define CK(h, call)                                                                              \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess)                                                                  \
+            return (h)->fail("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+    } while (0)
+#define NK(h, call)                                                                                       \
+    do {                                                                                                  \
+        ncclResult_t r__ = (call);                                                                        \
+        if (r__ != ncclSuccess)                                                                           \
+            return (h)->fail("%s:%d %s: %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r__));      \
+    } while (0)
+#define NEED(h)                                  \
+    if (!(h)) return 1;                          \
+    CK(h, cudaSetDevice((h)->device))
+
+namespace {
+
+int ensure_events(ldagpu_handle h, size_t n)
+{
+    while (h->events.size() < n) {
+        cudaEvent_t e;
+        CK(h, cudaEventCreate(&e));
+        h->events.push_back(e);
+    }
+    return 0;
+}
+
+int ensure_theta(ldagpu_handle h)
+{
+    if (h->theta.p) return 0;
+    CK(h, h->theta.alloc((size_t)std::max<int64_t>(h->dm.D, 1) * h->dm.Ks));
+    CK(h, cudaMemsetAsync(h->theta.p, 0, sizeof(float) * h->theta.n, h->stream));
+    return 0;
+}
+
+int step_theta(ldagpu_handle h)
+{
+    if (ensure_theta(h)) return 1;
+    CK(h, cudaMemsetAsync(h->counter.p, 0, sizeof(unsigned long long), h->stream));
+    ThetaArgs a{};
+    a.dm = h->dm; a.doc_off = h->doc_off.p; a.z = h->z.p; a.alpha = h->alpha_f.p; a.theta = h->theta.p;
+    a.work_counter = h->counter.p;
+    a.seed_lo = (uint32_t)h->seed; a.seed_hi = (uint32_t)(h->seed >> 32); a.sweep = (uint32_t)h->iteration;
+    CK(h, launch_theta(a, h->sm_count, h->stream));
+    h->last_launches += 1;
+    return 0;
+}
+
+int step_z(ldagpu_handle h)
+{
+    CK(h, cudaMemsetAsync(h->counter.p, 0, sizeof(unsigned long long), h->stream));
+    ZArgs a{};
+    a.dm = h->dm; a.doc_off = h->doc_off.p; a.tokens = h->tokens.p; a.z = h->z.p; a.phiT = h->phiT.p;
+    a.theta = h->theta.p; a.alpha = h->alpha_f.p; a.item_doc = h->item_doc.p; a.item_begin = h->item_begin.p;
+    a.n_items = h->n_items; a.work_counter = h->counter.p;
+    a.seed_lo = (uint32_t)h->seed; a.seed_hi = (uint32_t)(h->seed >> 32); a.sweep = (uint32_t)h->iteration;
+    if (h->scheme == LDAGPU_SCHEME_GGS) {
+        if (!h->theta.p) return h->fail("GGS z-step needs theta: call ldagpu_sample_theta or ldagpu_set_theta first");
+        CK(h, launch_z_ggs(a, h->sm_count, h->stream));
+    } else {
+        CK(h, launch_z_pcgs(a, h->sm_count, h->stream));
+    }
+    if (h->n_items) { h->last_launches += 1; h->last_zk_launches += 1; }
+    return 0;
+}
+
+int step_counts_local(ldagpu_handle h)
+{
+    CK(h, launch_counts(h->dm, h->tokens.p, h->z.p, h->n_wk.p, h->n_k.p, h->sm_count, h->stream));
+    h->last_launches += 1;
+    return 0;
+}
+
+int step_counts_exchange(ldagpu_handle h)
+{
+    if (h->world == 1) return 0;
+    const size_t slice = (size_t)(h->dm.Vp / h->world) * h->dm.Ks;
+    NK(h, g_nccl.ReduceScatter(h->n_wk.p, h->n_wk.p + (size_t)h->rank * slice, slice, ncclInt32, ncclSum, h->comm, h->stream));
+    NK(h, g_nccl.AllReduce(h->n_k.p, h->n_k.p, (size_t)h->dm.Ks, ncclInt32, ncclSum, h->comm, h->stream));
+    return 0;
+}
+
+// ev != nullptr: record events after draw+segments, segment all-gather, normalise, Phi all-gather
+int step_phi(ldagpu_handle h, bool accumulate_mean, cudaEvent_t *ev)
+{
+    const uint32_t lo = (uint32_t)h->seed, hi = (uint32_t)(h->seed >> 32);
+    CK(h, launch_phi_draw(h->dm, h->n_wk.p, h->beta, h->phiT.p, h->partial.p, h->row0, h->row1, lo, hi,
+                          (uint32_t)h->iteration, h->stream));
+    CK(h, launch_phi_segment_sums(h->dm, h->partial.p, h->seg.p, h->seg0, h->seg1, h->stream));
+    h->last_launches += 2;
+    if (ev) CK(h, cudaEventRecord(ev[0], h->stream));
+    if (h->world > 1) {
+        const size_t per = (size_t)(PHI_SEGMENTS / h->world) * h->dm.Ks;
+        NK(h, g_nccl.AllGather(h->seg.p + (size_t)h->rank * per, h->seg.p, per, ncclDouble, h->comm, h->stream));
+    }
+    if (ev) CK(h, cudaEventRecord(ev[1], h->stream));
+    double *mean = nullptr;
+    if (accumulate_mean) {
+        if (!h->phi_mean.p) {
+            CK(h, h->phi_mean.alloc((size_t)h->dm.Vp * h->dm.Ks));
+            CK(h, cudaMemsetAsync(h->phi_mean.p, 0, sizeof(double) * h->phi_mean.n, h->stream));
+        }
+        mean = h->phi_mean.p;
+    }
+    CK(h, launch_phi_normalise(h->dm, h->seg.p, h->topic_sum.p, h->phiT.p, mean, h->row0, h->row1, h->stream));
+    h->last_launches += 1;
+    if (ev) CK(h, cudaEventRecord(ev[2], h->stream));
+    if (h->world > 1) {
+        const size_t slice = (size_t)(h->dm.Vp / h->world) * h->dm.Ks;
+        NK(h, g_nccl.AllGather(h->phiT.p + (size_t)h->rank * slice, h->phiT.p, slice, ncclFloat, h->comm, h->stream));
+    }
+    if (ev) CK(h, cudaEventRecord(ev[3], h->stream));
+    return 0;
+}
+
+bool mean_this_iteration(ldagpu_handle h)
+{
+    // UPL:1350-1352 samplePhiThisIteration()
+    return h->mean_burn_in > 0 && h->iteration > h->mean_burn_in && h->mean_thin > 0 &&
+           h->iteration % h->mean_thin == 0;
+}
+
+int sync_check(ldagpu_handle h)
+{
+    CK(h, cudaStreamSynchronize(h->stream));
+    CK(h, cudaGetLastError());
+    return 0;
+}
+
+int run_sweeps(ldagpu_handle h, int32_t n, bool with_phi, int32_t *done)
+{
+    h->last_zk_ms = 0; h->last_zk_launches = 0; h->last_launches = 0;
+    if (done) *done = 0;
+    if (n <= 0) return 0;
+    if (ensure_events(h, (size_t)n * EV_PER_SWEEP)) return 1;
+    int32_t ran = 0;
+    for (int32_t s = 0; s < n; ++s) {
+        if (h->abort_flag.load(std::memory_order_relaxed)) break;
+        cudaEvent_t *ev = h->events.data() + (size_t)s * EV_PER_SWEEP;
+        h->iteration += 1;
+        CK(h, cudaEventRecord(ev[0], h->stream));
+        if (h->scheme == LDAGPU_SCHEME_GGS && step_theta(h)) return 1;
+        CK(h, cudaEventRecord(ev[1], h->stream));
+        if (step_z(h)) return 1;
+        CK(h, cudaEventRecord(ev[2], h->stream));
+        if (step_counts_local(h)) return 1;
+        CK(h, cudaEventRecord(ev[3], h->stream));
+        if (step_counts_exchange(h)) return 1;
+        CK(h, cudaEventRecord(ev[4], h->stream));
+        if (with_phi) {
+            bool acc = mean_this_iteration(h);
+            if (step_phi(h, acc, ev + 5)) return 1;
+            if (acc) h->n_sampled_phi += 1;   // GGS:168-170
+        } else {
+            for (int i = 5; i < EV_PER_SWEEP; ++i) CK(h, cudaEventRecord(ev[i], h->stream));
+        }
+        ++ran;
+    }
+    if (sync_check(h)) return 1;
+    for (int32_t s = 0; s < ran; ++s) {
+        cudaEvent_t *ev = h->events.data() + (size_t)s * EV_PER_SWEEP;
+        float ms[EV_PER_SWEEP - 1];
+        for (int i = 0; i + 1 < EV_PER_SWEEP; ++i) CK(h, cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+        h->t_z += ms[0] + ms[1];
+        h->last_zk_ms += ms[1];
+        h->t_counts += ms[2];
+        h->t_comm += ms[3] + ms[5] + ms[7];
+        h->t_phi += ms[4] + ms[6];
+    }
+    if (done) *done = ran;
+    return 0;
+}
+
+int build_items(ldagpu_handle h)
+{
+    const std::vector<int64_t> &off = h->h_doc_off;
+    const int64_t D = h->dm.D;
+    std::vector<int32_t> item_doc;
+    std::vector<int64_t> item_begin;
+    if (h->scheme == LDAGPU_SCHEME_GGS) {
+        // documents split freely into chunks: tokens are independent given theta (GGS:97-101)
+        for (int64_t d = 0; d < D; ++d)
+            for (int64_t t = off[d]; t < off[d + 1]; t += GGS_CHUNK) {
+                item_doc.push_back((int32_t)d);
+                item_begin.push_back(t);
+            }
+    } else {
+        // PCGS is sequential inside a document: one item per document, longest first
+        item_doc.resize((size_t)D);
+        std::iota(item_doc.begin(), item_doc.end(), 0);
+        std::stable_sort(item_doc.begin(), item_doc.end(), [&](int32_t a, int32_t b) {
+            return off[a + 1] - off[a] > off[b + 1] - off[b];
+        });
+        item_begin.assign(1, 0);
+    }
+    h->n_items = (int64_t)item_doc.size();
+    CK(h, h->item_doc.alloc(std::max<size_t>(item_doc.size(), 1)));
+    CK(h, h->item_begin.alloc(std::max<size_t>(item_begin.size(), 1)));
+    if (!item_doc.empty())
+        CK(h, cudaMemcpy(h->item_doc.p, item_doc.data(), sizeof(int32_t) * item_doc.size(), cudaMemcpyHostToDevice));
+    if (!item_begin.empty())
+        CK(h, cudaMemcpy(h->item_begin.p, item_begin.data(), sizeof(int64_t) * item_begin.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int validate_z(ldagpu_handle h)
+{
+    CK(h, launch_validate(h->dm, nullptr, h->z.p, h->bad.p, h->stream));
+    int bad = 0;
+    CK(h, cudaMemcpyAsync(&bad, h->bad.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (bad) return h->fail("topic indicator out of range [0, %d)", h->dm.K);   // UPL:475-481 throws
+    return 0;
+}
+
+double lgamma_stirling_host(double z)
+{
+    int shift = 0;
+    while (z < 2) { z++; shift++; }
+    double r = 0.5 * std::log(2 * M_PI) + (z - 0.5) * std::log(z) - z + 1 / (12 * z) - 1 / (360 * z * z * z) +
+               1 / (1260 * z * z * z * z * z);
+    while (shift > 0) { shift--; z--; r -= std::log(z); }
+    return r;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char *ldagpu_version(void) { return "libldagpu 0.1 (sm_100a; GGS + PCGS dense z-step, K <= 1024)"; }
+
+const char *ldagpu_last_error(ldagpu_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int ldagpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int ldagpu_create(int32_t K, int32_t V, int64_t D, const int64_t *doc_offsets, const int32_t *tokens,
+                  const double *alpha, double beta, uint64_t seed, int32_t scheme, int32_t device,
+                  int64_t doc_base, int64_t token_base, ldagpu_handle *out)
+{
+    if (out) *out = nullptr;
+    auto bail = [&](const std::string &m) { g_create_error = m; return 1; };
+    if (!out || !doc_offsets || (!tokens && D > 0 && doc_offsets[D] > 0) || !alpha) return bail("null argument");
+    if (K < 1 || V < 1 || D < 0) return bail("K, V must be >= 1 and D >= 0");
+    if (scheme != LDAGPU_SCHEME_GGS && scheme != LDAGPU_SCHEME_PCGS) return bail("unknown scheme");
+    if ((K + TILE - 1) / TILE > MAX_REG_TILES) return bail("K > 1024 is not supported by the dense z-step yet");
+    if (!(beta > 0.0)) return bail("beta must be > 0");   // ParallelRandoms.java:61-63
+    for (int k = 0; k < K; ++k)
+        if (!(alpha[k] > 0.0)) return bail("alpha must be > 0");
+    if (doc_offsets[0] != 0) return bail("doc_offsets[0] must be 0");
+    for (int64_t d = 0; d < D; ++d)
+        if (doc_offsets[d + 1] < doc_offsets[d]) return bail("doc_offsets must be non-decreasing");
+    int ndev = ldagpu_device_count();
+    if (ndev == 0) return bail("no CUDA device: libldagpu has no CPU fallback");
+    if (device < 0 || device >= ndev) return bail("device ordinal out of range");
+
+    ldagpu_handle h = new ldagpu_handle_s();
+    auto fail_out = [&]() { g_create_error = h->err; ldagpu_destroy(h); return 1; };
+    h->device = device;
+    h->scheme = scheme;
+    h->beta = beta;
+    h->seed = seed;
+    h->alpha.assign(alpha, alpha + K);
+    h->alpha_sum = 0.0;
+    for (int k = 0; k < K; ++k) h->alpha_sum += alpha[k];   // sequential, as MSL:139-143
+    Dims &dm = h->dm;
+    dm.K = K; dm.Ks = (int32_t)round_up(K, 32); dm.NT = (K + TILE - 1) / TILE;
+    dm.V = V; dm.Vp = (int32_t)round_up(V, PHI_ROW_BLOCK * PHI_SEGMENTS);
+    dm.D = D; dm.N = doc_offsets[D]; dm.doc_base = doc_base; dm.token_base = token_base;
+    h->D_global = D;
+    h->row0 = 0; h->row1 = dm.Vp; h->seg0 = 0; h->seg1 = PHI_SEGMENTS;
+    h->h_doc_off.assign(doc_offsets, doc_offsets + D + 1);
+
+    auto body = [&]() -> int {
+        CK(h, cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CK(h, cudaGetDeviceProperties(&prop, device));
+        h->sm_count = prop.multiProcessorCount;
+        CK(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        const size_t N1 = (size_t)std::max<int64_t>(dm.N, 1);
+        CK(h, h->doc_off.alloc((size_t)D + 1));
+        CK(h, h->tokens.alloc(N1 + 4));
+        CK(h, h->z.alloc(N1 + 4));
+        CK(h, h->phiT.alloc((size_t)dm.Vp * dm.Ks));
+        CK(h, h->n_wk.alloc((size_t)dm.Vp * dm.Ks));
+        CK(h, h->n_k.alloc((size_t)dm.Ks));
+        CK(h, h->alpha_f.alloc((size_t)dm.Ks));
+        CK(h, h->alpha_d.alloc((size_t)dm.Ks));
+        CK(h, h->partial.alloc((size_t)(dm.Vp / PHI_ROW_BLOCK) * dm.Ks));
+        CK(h, h->seg.alloc((size_t)PHI_SEGMENTS * dm.Ks));
+        CK(h, h->topic_sum.alloc((size_t)dm.Ks));
+        CK(h, h->red.alloc((size_t)N_PARTIALS * 2));
+        CK(h, h->red_out.alloc(8));
+        CK(h, h->counter.alloc(1));
+        CK(h, h->bad.alloc(1));
+        CK(h, cudaMemcpy(h->doc_off.p, doc_offsets, sizeof(int64_t) * ((size_t)D + 1), cudaMemcpyHostToDevice));
+        CK(h, cudaMemset(h->tokens.p, 0, sizeof(int32_t) * h->tokens.n));
+        CK(h, cudaMemset(h->z.p, 0, sizeof(int32_t) * h->z.n));
+        if (dm.N) CK(h, cudaMemcpy(h->tokens.p, tokens, sizeof(int32_t) * (size_t)dm.N, cudaMemcpyHostToDevice));
+        CK(h, cudaMemset(h->phiT.p, 0, sizeof(float) * h->phiT.n));
+        CK(h, cudaMemset(h->n_wk.p, 0, sizeof(int32_t) * h->n_wk.n));
+        CK(h, cudaMemset(h->n_k.p, 0, sizeof(int32_t) * h->n_k.n));
+        CK(h, cudaMemset(h->partial.p, 0, sizeof(double) * h->partial.n));
+        CK(h, cudaMemset(h->seg.p, 0, sizeof(double) * h->seg.n));
+        std::vector<float> af((size_t)dm.Ks, 0.0f);
+        std::vector<double> ad((size_t)dm.Ks, 0.0);
+        for (int k = 0; k < K; ++k) { af[k] = (float)alpha[k]; ad[k] = alpha[k]; }
+        CK(h, cudaMemcpy(h->alpha_f.p, af.data(), sizeof(float) * af.size(), cudaMemcpyHostToDevice));
+        CK(h, cudaMemcpy(h->alpha_d.p, ad.data(), sizeof(double) * ad.size(), cudaMemcpyHostToDevice));
+        // type ids must be inside the alphabet (UPL:360 numTypes = alphabet.size())
+        CK(h, launch_validate(dm, h->tokens.p, nullptr, h->bad.p, h->stream));
+        int bad = 0;
+        CK(h, cudaMemcpyAsync(&bad, h->bad.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        if (bad) return h->fail("token type id out of range [0, %d)", V);
+        if (build_items(h)) return 1;
+        if (scheme == LDAGPU_SCHEME_GGS && ensure_theta(h)) return 1;
+        return sync_check(h);
+    };
+    if (body()) return fail_out();
+    *out = h;
+    return 0;
+}
+
+int ldagpu_destroy(ldagpu_handle h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+    h->doc_off.release(); h->item_begin.release(); h->tokens.release(); h->z.release(); h->n_wk.release();
+    h->n_k.release(); h->item_doc.release(); h->scratch_i32.release(); h->phiT.release(); h->theta.release();
+    h->alpha_f.release(); h->alpha_d.release(); h->partial.release(); h->seg.release(); h->topic_sum.release();
+    h->phi_mean.release(); h->red.release(); h->red_out.release(); h->scratch_f64.release();
+    h->counter.release(); h->bad.release();
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+int ldagpu_comm_unique_id(void *id128)
+{
+    if (!id128) return 1;
+    if (!g_nccl.load()) { g_create_error = g_nccl.err; return 1; }
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return 1; }
+    std::memcpy(id128, &id, sizeof id);
+    return 0;
+}
+
+int ldagpu_comm_init(ldagpu_handle h, int32_t rank, int32_t world, const void *id128)
+{
+    NEED(h);
+    if (world < 1 || rank < 0 || rank >= world) return h->fail("bad rank/world");
+    if (world == 1) return 0;
+    if (PHI_SEGMENTS % world != 0) return h->fail("world size must divide %d", PHI_SEGMENTS);
+    if (!g_nccl.load()) return h->fail("%s", g_nccl.err.c_str());
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof id);
+    NK(h, g_nccl.CommInitRank(&h->comm, world, id, rank));
+    h->rank = rank;
+    h->world = world;
+    const int32_t rows = h->dm.Vp / world;
+    h->row0 = rank * rows;
+    h->row1 = h->row0 + rows;
+    h->seg0 = rank * (PHI_SEGMENTS / world);
+    h->seg1 = h->seg0 + PHI_SEGMENTS / world;
+    // global document count for the D * lgS(alphaSum) term of the log-likelihood
+    DevBuf<long long> tmp;
+    CK(h, tmp.alloc(1));
+    long long d = h->dm.D;
+    CK(h, cudaMemcpyAsync(tmp.p, &d, sizeof d, cudaMemcpyHostToDevice, h->stream));
+    NK(h, g_nccl.AllReduce(tmp.p, tmp.p, 1, ncclInt64, ncclSum, h->comm, h->stream));
+    CK(h, cudaMemcpyAsync(&d, tmp.p, sizeof d, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    tmp.release();
+    h->D_global = d;
+    return 0;
+}
+
+static int refresh_counts_and_phi(ldagpu_handle h, bool redraw_phi)
+{
+    if (step_counts_local(h) || step_counts_exchange(h)) return 1;
+    if (redraw_phi && step_phi(h, false, nullptr)) return 1;
+    return sync_check(h);
+}
+
+int ldagpu_init_z_java_random(ldagpu_handle h, int32_t seed)
+{
+    NEED(h);
+    // the stream of nextInt(K) is sequential over the whole corpus: skip the draws of the shards before ours
+    JavaRandom r((int64_t)seed);
+    for (int64_t i = 0; i < h->dm.token_base; ++i) (void)r.nextInt(h->dm.K);
+    std::vector<int32_t> z((size_t)h->dm.N);
+    for (int64_t i = 0; i < h->dm.N; ++i) z[(size_t)i] = r.nextInt(h->dm.K);
+    if (h->dm.N) CK(h, cudaMemcpyAsync(h->z.p, z.data(), sizeof(int32_t) * z.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return refresh_counts_and_phi(h, true);   // initialSamplePhi, UPL:450
+}
+
+int ldagpu_set_z(ldagpu_handle h, const int32_t *z, int32_t redraw_phi)
+{
+    NEED(h);
+    if (!z && h->dm.N) return h->fail("null z");
+    if (h->dm.N) CK(h, cudaMemcpyAsync(h->z.p, z, sizeof(int32_t) * (size_t)h->dm.N, cudaMemcpyHostToDevice, h->stream));
+    if (validate_z(h)) return 1;
+    return refresh_counts_and_phi(h, redraw_phi != 0);   // UPL:1842
+}
+
+int ldagpu_get_z(ldagpu_handle h, int32_t *z)
+{
+    NEED(h);
+    if (h->dm.N) CK(h, cudaMemcpyAsync(z, h->z.p, sizeof(int32_t) * (size_t)h->dm.N, cudaMemcpyDeviceToHost, h->stream));
+    return sync_check(h);
+}
+
+int ldagpu_sweep(ldagpu_handle h, int32_t n, int32_t *done)
+{
+    NEED(h);
+    return run_sweeps(h, n, true, done);
+}
+
+int ldagpu_sample_z_given_phi(ldagpu_handle h, int32_t n, int32_t *done)
+{
+    NEED(h);
+    return run_sweeps(h, n, false, done);
+}
+
+int ldagpu_next_iteration(ldagpu_handle h) { NEED(h); h->iteration += 1; return 0; }
+int ldagpu_get_iteration(ldagpu_handle h, int32_t *it) { if (!h || !it) return 1; *it = h->iteration; return 0; }
+int ldagpu_set_iteration(ldagpu_handle h, int32_t it) { if (!h) return 1; h->iteration = it; return 0; }
+
+int ldagpu_sample_theta(ldagpu_handle h)
+{
+    NEED(h);
+    if (step_theta(h)) return 1;
+    return sync_check(h);
+}
+int ldagpu_sample_z(ldagpu_handle h)
+{
+    NEED(h);
+    if (step_z(h)) return 1;
+    return sync_check(h);
+}
+int ldagpu_rebuild_counts(ldagpu_handle h)
+{
+    NEED(h);
+    return refresh_counts_and_phi(h, false);
+}
+int ldagpu_sample_phi(ldagpu_handle h)
+{
+    NEED(h);
+    bool acc = mean_this_iteration(h);
+    if (step_phi(h, acc, nullptr)) return 1;
+    if (acc) h->n_sampled_phi += 1;
+    return sync_check(h);
+}
+
+int ldagpu_get_type_topic_counts(ldagpu_handle h, int32_t *out)
+{
+    NEED(h);
+    const size_t cells = (size_t)h->dm.V * h->dm.K;
+    if (h->world > 1) {
+        // every rank holds the global counts of its vocabulary slice only: gather the slices
+        const size_t slice = (size_t)(h->dm.Vp / h->world) * h->dm.Ks;
+        NK(h, g_nccl.AllGather(h->n_wk.p + (size_t)h->rank * slice, h->n_wk.p, slice, ncclInt32, h->comm, h->stream));
+    }
+    CK(h, h->scratch_i32.alloc(cells));
+    CK(h, launch_export_counts(h->dm, h->n_wk.p, h->scratch_i32.p, h->stream));
+    CK(h, cudaMemcpyAsync(out, h->scratch_i32.p, sizeof(int32_t) * cells, cudaMemcpyDeviceToHost, h->stream));
+    int rc = sync_check(h);
+    h->scratch_i32.release();
+    return rc;
+}
+
+int ldagpu_get_topic_totals(ldagpu_handle h, int32_t *n_k)
+{
+    NEED(h);
+    CK(h, cudaMemcpyAsync(n_k, h->n_k.p, sizeof(int32_t) * (size_t)h->dm.K, cudaMemcpyDeviceToHost, h->stream));
+    return sync_check(h);
+}
+
+int ldagpu_get_doc_topic_counts(ldagpu_handle h, int32_t *n_dk)
+{
+    NEED(h);
+    const size_t cells = (size_t)h->dm.D * h->dm.K;
+    if (cells == 0) return 0;
+    CK(h, h->scratch_i32.alloc(cells));
+    CK(h, launch_doc_topic_counts(h->dm, h->doc_off.p, h->z.p, h->scratch_i32.p, h->stream));
+    CK(h, cudaMemcpyAsync(n_dk, h->scratch_i32.p, sizeof(int32_t) * cells, cudaMemcpyDeviceToHost, h->stream));
+    int rc = sync_check(h);
+    h->scratch_i32.release();
+    return rc;
+}
+
+int ldagpu_get_phi(ldagpu_handle h, double *phi)
+{
+    NEED(h);
+    const size_t cells = (size_t)h->dm.V * h->dm.K;
+    CK(h, h->scratch_f64.alloc(cells));
+    CK(h, launch_export_phi(h->dm, h->phiT.p, h->scratch_f64.p, h->stream));
+    CK(h, cudaMemcpyAsync(phi, h->scratch_f64.p, sizeof(double) * cells, cudaMemcpyDeviceToHost, h->stream));
+    int rc = sync_check(h);
+    h->scratch_f64.release();
+    return rc;
+}
+
+int ldagpu_set_phi(ldagpu_handle h, const double *phi)
+{
+    NEED(h);
+    const size_t cells = (size_t)h->dm.V * h->dm.K;
+    CK(h, h->scratch_f64.alloc(cells));
+    CK(h, cudaMemcpyAsync(h->scratch_f64.p, phi, sizeof(double) * cells, cudaMemcpyHostToDevice, h->stream));
+    CK(h, launch_import_phi(h->dm, h->scratch_f64.p, h->phiT.p, h->stream));
+    int rc = sync_check(h);
+    h->scratch_f64.release();
+    // UPL:1897-1903: setPhi resets the running mean
+    if (h->phi_mean.p) CK(h, cudaMemset(h->phi_mean.p, 0, sizeof(double) * h->phi_mean.n));
+    h->n_sampled_phi = 0;
+    return rc;
+}
+
+int ldagpu_set_phi_mean_schedule(ldagpu_handle h, int32_t burn_in, int32_t thin)
+{
+    if (!h) return 1;
+    h->mean_burn_in = burn_in;
+    h->mean_thin = thin < 1 ? 1 : thin;
+    return 0;
+}
+
+int ldagpu_get_phi_mean(ldagpu_handle h, double *phi_mean, int32_t *n_sampled)
+{
+    NEED(h);
+    if (n_sampled) *n_sampled = h->n_sampled_phi;
+    if (h->n_sampled_phi == 0 || !h->phi_mean.p) return 0;   // UPL:1955-1958 returns null
+    if (h->world > 1) {
+        const size_t slice = (size_t)(h->dm.Vp / h->world) * h->dm.Ks;
+        NK(h, g_nccl.AllGather(h->phi_mean.p + (size_t)h->rank * slice, h->phi_mean.p, slice, ncclDouble, h->comm, h->stream));
+    }
+    const size_t cells = (size_t)h->dm.V * h->dm.K;
+    CK(h, h->scratch_f64.alloc(cells));
+    CK(h, launch_export_mean(h->dm, h->phi_mean.p, 1.0 / (double)h->n_sampled_phi, h->scratch_f64.p, h->stream));
+    CK(h, cudaMemcpyAsync(phi_mean, h->scratch_f64.p, sizeof(double) * cells, cudaMemcpyDeviceToHost, h->stream));
+    int rc = sync_check(h);
+    h->scratch_f64.release();
+    return rc;
+}
+
+int ldagpu_get_theta(ldagpu_handle h, double *theta)
+{
+    NEED(h);
+    if (ensure_theta(h)) return 1;
+    const size_t cells = (size_t)h->dm.D * h->dm.K;
+    if (cells == 0) return 0;
+    CK(h, h->scratch_f64.alloc(cells));
+    CK(h, launch_export_theta(h->dm, h->theta.p, h->scratch_f64.p, h->stream));
+    CK(h, cudaMemcpyAsync(theta, h->scratch_f64.p, sizeof(double) * cells, cudaMemcpyDeviceToHost, h->stream));
+    int rc = sync_check(h);
+    h->scratch_f64.release();
+    return rc;
+}
+
+int ldagpu_set_theta(ldagpu_handle h, const double *theta)
+{
+    NEED(h);
+    if (ensure_theta(h)) return 1;
+    const size_t cells = (size_t)h->dm.D * h->dm.K;
+    if (cells == 0) return 0;
+    CK(h, h->scratch_f64.alloc(cells));
+    CK(h, cudaMemcpyAsync(h->scratch_f64.p, theta, sizeof(double) * cells, cudaMemcpyHostToDevice, h->stream));
+    CK(h, launch_import_theta(h->dm, h->scratch_f64.p, h->theta.p, h->stream));
+    int rc = sync_check(h);
+    h->scratch_f64.release();
+    return rc;
+}
+
+int ldagpu_log_likelihood(ldagpu_handle h, double *ll)
+{
+    NEED(h);
+    CK(h, launch_ll_doc(h->dm, h->doc_off.p, h->z.p, h->alpha_d.p, h->alpha_sum, h->red.p, N_PARTIALS, h->sm_count, h->stream));
+    CK(h, launch_sum_partials(h->red.p, N_PARTIALS, 1, h->red_out.p, h->stream));
+    CK(h, launch_ll_type(h->dm, h->n_wk.p, h->beta, h->row0, h->row1, h->red.p, N_PARTIALS, h->stream));
+    CK(h, launch_sum_partials(h->red.p, N_PARTIALS, 2, h->red_out.p + 1, h->stream));
+    if (h->world > 1) NK(h, g_nccl.AllReduce(h->red_out.p, h->red_out.p, 3, ncclDouble, ncclSum, h->comm, h->stream));
+    double part[3];
+    std::vector<int32_t> nk((size_t)h->dm.K);
+    CK(h, cudaMemcpyAsync(part, h->red_out.p, sizeof part, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(nk.data(), h->n_k.p, sizeof(int32_t) * nk.size(), cudaMemcpyDeviceToHost, h->stream));
+    if (sync_check(h)) return 1;
+    // UPL:1698,1724-1749: parameter-sum terms, added once
+    const double bV = h->beta * h->dm.V;
+    double v = part[0] + (double)h->D_global * lgamma_stirling_host(h->alpha_sum) + part[1];
+    for (int k = 0; k < h->dm.K; ++k) v -= lgamma_stirling_host(bV + nk[(size_t)k]);
+    v += lgamma_stirling_host(bV) * h->dm.K;
+    v -= lgamma_stirling_host(h->beta) * part[2];
+    if (std::isnan(v) || std::isinf(v)) v = 0.0;   // UPL:1730-1755 returns 0
+    *ll = v;
+    return 0;
+}
+
+int ldagpu_log_posterior(ldagpu_handle h, double *lp)
+{
+    NEED(h);
+    if (ensure_theta(h)) return 1;
+    CK(h, launch_lp_tokens(h->dm, h->tokens.p, h->z.p, h->phiT.p, h->red.p, N_PARTIALS, h->stream));
+    CK(h, launch_sum_partials(h->red.p, N_PARTIALS, 1, h->red_out.p, h->stream));
+    CK(h, launch_lp_theta(h->dm, h->doc_off.p, h->z.p, h->theta.p, h->alpha_d.p, h->red.p, N_PARTIALS, h->sm_count, h->stream));
+    CK(h, launch_sum_partials(h->red.p, N_PARTIALS, 1, h->red_out.p + 1, h->stream));
+    CK(h, launch_lp_phi(h->dm, h->phiT.p, h->beta, h->row0, h->row1, h->red.p, N_PARTIALS, h->stream));
+    CK(h, launch_sum_partials(h->red.p, N_PARTIALS, 1, h->red_out.p + 2, h->stream));
+    if (h->world > 1) NK(h, g_nccl.AllReduce(h->red_out.p, h->red_out.p, 3, ncclDouble, ncclSum, h->comm, h->stream));
+    double part[3];
+    CK(h, cudaMemcpyAsync(part, h->red_out.p, sizeof part, cudaMemcpyDeviceToHost, h->stream));
+    if (sync_check(h)) return 1;
+    *lp = part[0] + part[1] + part[2];
+    return 0;
+}
+
+int ldagpu_abort(ldagpu_handle h) { if (!h) return 1; h->abort_flag.store(1); return 0; }
+int ldagpu_get_abort(ldagpu_handle h, int32_t *aborted) { if (!h || !aborted) return 1; *aborted = h->abort_flag.load(); return 0; }
+
+int ldagpu_get_timers(ldagpu_handle h, double *z_ms, double *counts_ms, double *phi_ms, double *comm_ms)
+{
+    if (!h) return 1;
+    if (z_ms) *z_ms = h->t_z;
+    if (counts_ms) *counts_ms = h->t_counts;
+    if (phi_ms) *phi_ms = h->t_phi;
+    if (comm_ms) *comm_ms = h->t_comm;
+    return 0;
+}
+
+int ldagpu_get_last_call_stats(ldagpu_handle h, double *z_kernel_ms, int64_t *z_kernel_launches, int64_t *total_launches)
+{
+    if (!h) return 1;
+    if (z_kernel_ms) *z_kernel_ms = h->last_zk_ms;
+    if (z_kernel_launches) *z_kernel_launches = h->last_zk_launches;
+    if (total_launches) *total_launches = h->last_launches;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,483 @@
+// kernels_misc.cu -- K3 (count rebuild), K4 (log-likelihood, log-posterior) and accessor kernels.
+//
+// Replaces (reference, src/main/java/cc/mallet/topics/):
+//   K3  UncollapsedParallelLDA.java:1547-1557 (+-1 deltas), :1107-1221 (updateCounts merge),
+//       :1797-1830 (setZIndicators rebuild), :471-482 (updateTypeTopicCount)
+//   K4  UncollapsedParallelLDA.java:1644-1758 (modelLogLikelihood), :1573-1634 (computeLogPosterior)
+//   accessors  UncollapsedParallelLDA.java:226-234 (getTypeTopicCounts), ModifiedSimpleLDA.java:536-547
+//       (getDocumentTopicMatrix), UncollapsedParallelLDA.java:1946-1966 (getPhi / getPhiMeans)
+#include "common.cuh"
+#include "contract_math.cuh"
+
+namespace ldagpu {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------
+// K3: n_wk[w][k] = #{i : w_i = w, z_i = k},  n_k = column sums.  Integer, exact.
+// int4 loads of (w, z); equal neighbours merged in the thread, then equal keys merged across
+// the warp (match.any + redux) so one atomic goes out per distinct (w, k) per warp step.
+// ---------------------------------------------------------------------------------------
+constexpr int CNT_THREADS = 256;
+
+__device__ __forceinline__ void warp_aggregated_add(int32_t *n_wk, unsigned long long key, int c)
+{
+    // lanes with nothing to add use a key no real cell can have, distinct per lane
+    unsigned m = __match_any_sync(FULL, key);
+    int total = __reduce_add_sync(m, c);
+    if (total > 0 && (int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&n_wk[key], total);
+}
+
+__global__ void __launch_bounds__(CNT_THREADS)
+counts_kernel(Dims dm, const int32_t *__restrict__ tokens, const int32_t *__restrict__ z,
+              int32_t *__restrict__ n_wk, int32_t *__restrict__ n_k, int use_smem_hist)
+{
+    extern __shared__ int32_t s_hist[];
+    if (use_smem_hist) {
+        for (int i = threadIdx.x; i < dm.K; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t n4 = dm.N / 4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // all lanes of a warp iterate together (match.any needs the whole warp)
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane;
+    for (int64_t base = first; base < n4; base += stride) {
+        const int64_t i = base + lane;
+        const bool ok = i < n4;
+        int4 w4 = ok ? __ldg(reinterpret_cast<const int4 *>(tokens) + i) : make_int4(0, 0, 0, 0);
+        int4 z4 = ok ? __ldg(reinterpret_cast<const int4 *>(z) + i) : make_int4(0, 0, 0, 0);
+        unsigned long long key[4];
+        int c[4];
+        const int ww[4] = {w4.x, w4.y, w4.z, w4.w};
+        const int zz[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            key[s] = (unsigned long long)ww[s] * (unsigned long long)dm.Ks + (unsigned long long)zz[s];
+            c[s] = ok ? 1 : 0;
+            if (ok) {
+                if (use_smem_hist) atomicAdd(&s_hist[zz[s]], 1);
+                else atomicAdd(&n_k[zz[s]], 1);
+            }
+        }
+        // merge equal neighbours inside the thread (documents are bags of words: equal types adjacent)
+#pragma unroll
+        for (int s = 3; s > 0; --s)
+            if (key[s] == key[s - 1]) { c[s - 1] += c[s]; c[s] = 0; }
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            unsigned long long kk = c[s] > 0 ? key[s] : (0xffffffff00000000ull | (unsigned)lane);
+            warp_aggregated_add(n_wk, kk, c[s]);
+        }
+    }
+    // scalar tail (N % 4 tokens), done by block 0
+    if (blockIdx.x == 0) {
+        for (int64_t i = n4 * 4 + threadIdx.x; i < dm.N; i += blockDim.x) {
+            atomicAdd(&n_wk[(size_t)tokens[i] * dm.Ks + z[i]], 1);
+            if (use_smem_hist) atomicAdd(&s_hist[z[i]], 1);
+            else atomicAdd(&n_k[z[i]], 1);
+        }
+    }
+    if (use_smem_hist) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < dm.K; i += blockDim.x)
+            if (s_hist[i]) atomicAdd(&n_k[i], s_hist[i]);
+    }
+}
+
+cudaError_t launch_counts(const Dims &dm, const int32_t *tokens, const int32_t *z, int32_t *n_wk,
+                          int32_t *n_k, int sm_count, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(n_wk, 0, sizeof(int32_t) * (size_t)dm.Vp * dm.Ks, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(n_k, 0, sizeof(int32_t) * (size_t)dm.Ks, st);
+    if (e != cudaSuccess) return e;
+    if (dm.N == 0) return cudaSuccess;
+    size_t smem = sizeof(int32_t) * (size_t)dm.K;
+    int use_smem = smem <= 48 * 1024;
+    int64_t need = (dm.N / 4 + CNT_THREADS - 1) / CNT_THREADS;
+    int64_t grid = (int64_t)sm_count * 8;
+    if (need < grid) grid = need;
+    if (grid < 1) grid = 1;
+    counts_kernel<<<(unsigned)grid, CNT_THREADS, use_smem ? smem : 0, st>>>(dm, tokens, z, n_wk, n_k, use_smem);
+    return cudaGetLastError();
+}
+
+__global__ void topic_totals_kernel(Dims dm, const int32_t *__restrict__ n_wk, int32_t *__restrict__ n_k)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= dm.K) return;
+    int acc = 0;
+    for (int w = blockIdx.y; w < dm.V; w += gridDim.y) acc += n_wk[(size_t)w * dm.Ks + k];
+    if (acc) atomicAdd(&n_k[k], acc);
+}
+cudaError_t launch_topic_totals(const Dims &dm, const int32_t *n_wk, int32_t *n_k, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(n_k, 0, sizeof(int32_t) * (size_t)dm.Ks, st);
+    if (e != cudaSuccess) return e;
+    dim3 grid((dm.K + 127) / 128, 64);
+    topic_totals_kernel<<<grid, 128, 0, st>>>(dm, n_wk, n_k);
+    return cudaGetLastError();
+}
+
+// getDocumentTopicMatrix: dense [D][K]
+__global__ void doc_topic_kernel(Dims dm, const int64_t *__restrict__ doc_off, const int32_t *__restrict__ z,
+                                 int32_t *__restrict__ n_dk)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t d = wid; d < dm.D; d += nw)
+        for (int64_t t = doc_off[d] + lane; t < doc_off[d + 1]; t += 32)
+            atomicAdd(&n_dk[(size_t)d * dm.K + z[t]], 1);
+}
+cudaError_t launch_doc_topic_counts(const Dims &dm, const int64_t *doc_off, const int32_t *z,
+                                    int32_t *n_dk, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(n_dk, 0, sizeof(int32_t) * (size_t)dm.D * dm.K, st);
+    if (e != cudaSuccess || dm.D == 0) return e;
+    int64_t grid = (dm.D + 7) / 8;
+    if (grid > 65535 * 16) grid = 65535 * 16;
+    doc_topic_kernel<<<(unsigned)grid, 256, 0, st>>>(dm, doc_off, z, n_dk);
+    return cudaGetLastError();
+}
+
+__global__ void validate_kernel(Dims dm, const int32_t *__restrict__ tokens, const int32_t *__restrict__ z, int *bad)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < dm.N; i += (int64_t)gridDim.x * blockDim.x) {
+        if (tokens && (tokens[i] < 0 || tokens[i] >= dm.V)) atomicOr(bad, 1);
+        if (z && (z[i] < 0 || z[i] >= dm.K)) atomicOr(bad, 2);
+    }
+}
+cudaError_t launch_validate(const Dims &dm, const int32_t *tokens, const int32_t *z, int *bad, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(bad, 0, sizeof(int), st);
+    if (e != cudaSuccess || dm.N == 0) return e;
+    int64_t grid = (dm.N + 255) / 256;
+    if (grid > 4096) grid = 4096;
+    validate_kernel<<<(unsigned)grid, 256, 0, st>>>(dm, tokens, z, bad);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// K4: log-likelihood (UncollapsedParallelLDA.java:1644-1758).
+// logGammaStirling is MALLET 2.0.8's Dirichlet.logGammaStirling restated (the jar is not in the
+// reference tree, pom.xml:130-141): shift up to >= 2, Stirling series, subtract the shifted logs.
+// fp64 throughout, contract ln; per-block partial sums, combined by sum_partials_kernel.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double lgamma_stirling(double z)
+{
+    int shift = 0;
+    while (z < 2.0) { z += 1.0; ++shift; }
+    const double zi = 1.0 / z;
+    const double z3 = zi * zi * zi;
+    double r = 0x1.d67f1c864beb5p-1 /* ln(2 pi)/2 */ + (z - 0.5) * c_ln<double>(z) - z + zi / 12.0 - z3 / 360.0 +
+               z3 * zi * zi / 1260.0;
+    while (shift > 0) { --shift; z -= 1.0; r -= c_ln<double>(z); }
+    return r;
+}
+
+constexpr int RED_THREADS = 256;
+
+// deterministic block reduction; result valid in thread 0
+__device__ __forceinline__ double block_sum(double v)
+{
+    __shared__ double s_red[RED_THREADS / 32];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_red[i];
+    return t;
+}
+
+// document part: sum_d [ sum_{k: n_dk>0} (lgS(alpha_k + n_dk) - lgS(alpha_k)) - lgS(alphaSum + N_d) ]
+__global__ void __launch_bounds__(RED_THREADS)
+ll_doc_kernel(Dims dm, const int64_t *__restrict__ doc_off, const int32_t *__restrict__ z,
+              const double *__restrict__ alpha, double alpha_sum, double *__restrict__ partials)
+{
+    extern __shared__ int32_t s_cnt[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    int32_t *cnt = s_cnt + (size_t)warp * dm.Ks;
+    for (int i = lane; i < dm.Ks; i += 32) cnt[i] = 0;
+    __syncwarp();
+    double acc = 0.0;
+    for (int64_t d = (int64_t)blockIdx.x * nwarp + warp; d < dm.D; d += (int64_t)gridDim.x * nwarp) {
+        const int64_t t0 = doc_off[d], t1 = doc_off[d + 1];
+        for (int64_t t = t0 + lane; t < t1; t += 32) atomicAdd(&cnt[z[t]], 1);
+        __syncwarp();
+        for (int k = lane; k < dm.K; k += 32) {
+            int c = cnt[k];
+            if (c > 0) {
+                acc += lgamma_stirling(alpha[k] + (double)c) - lgamma_stirling(alpha[k]);
+                cnt[k] = 0;
+            }
+        }
+        if (lane == 0) acc -= lgamma_stirling(alpha_sum + (double)(t1 - t0));
+        __syncwarp();
+    }
+    double t = block_sum(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+
+cudaError_t launch_ll_doc(const Dims &dm, const int64_t *doc_off, const int32_t *z,
+                          const double *alpha, double alpha_sum, double *partials, int n_partials,
+                          int sm_count, cudaStream_t st)
+{
+    (void)sm_count;
+    size_t smem = sizeof(int32_t) * (size_t)dm.Ks * (RED_THREADS / 32);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(ll_doc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    ll_doc_kernel<<<n_partials, RED_THREADS, smem, st>>>(dm, doc_off, z, alpha, alpha_sum, partials);
+    return cudaGetLastError();
+}
+
+// type part over rows [row0,row1): sum_{n_wk>0} lgS(beta + n_wk), and the count of such cells
+__global__ void __launch_bounds__(RED_THREADS)
+ll_type_kernel(Dims dm, const int32_t *__restrict__ n_wk, double beta, int32_t row0, int32_t row1,
+               double *__restrict__ partials)
+{
+    double acc = 0.0, nnz = 0.0;
+    const int64_t cells = (int64_t)(row1 - row0) * dm.Ks;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t w = row0 + (int32_t)(i / dm.Ks);
+        const int k = (int)(i % dm.Ks);
+        if (w >= dm.V || k >= dm.K) continue;
+        int c = n_wk[(size_t)w * dm.Ks + k];
+        if (c > 0) { acc += lgamma_stirling(beta + (double)c); nnz += 1.0; }
+    }
+    double t = block_sum(acc);
+    double u = block_sum(nnz);
+    if (threadIdx.x == 0) { partials[2 * blockIdx.x] = t; partials[2 * blockIdx.x + 1] = u; }
+}
+cudaError_t launch_ll_type(const Dims &dm, const int32_t *n_wk, double beta, int32_t row0,
+                           int32_t row1, double *partials, int n_partials, cudaStream_t st)
+{
+    ll_type_kernel<<<n_partials, RED_THREADS, 0, st>>>(dm, n_wk, beta, row0, row1, partials);
+    return cudaGetLastError();
+}
+
+// out[j] = sum_i partials[i*stride + j] for j < stride, sequential over i (deterministic)
+__global__ void sum_partials_kernel(const double *__restrict__ partials, int n, int stride, double *out)
+{
+    int j = threadIdx.x;
+    if (j >= stride) return;
+    double acc = 0.0;
+    for (int i = 0; i < n; ++i) acc += partials[(size_t)i * stride + j];
+    out[j] = acc;
+}
+cudaError_t launch_sum_partials(const double *partials, int n, int stride, double *out, cudaStream_t st)
+{
+    sum_partials_kernel<<<1, 32, 0, st>>>(partials, n, stride, out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// log-posterior (UncollapsedParallelLDA.java:1573-1634):
+//   sum_i ln(phi[z_i][w_i] + 1e-12) + sum_d sum_k (n_dk + alpha_k - 1) ln(theta_dk + 1e-12)
+//   + (beta - 1) sum_kv ln(phi_kv + 1e-12)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RED_THREADS)
+lp_tokens_kernel(Dims dm, const int32_t *__restrict__ tokens, const int32_t *__restrict__ z,
+                 const float *__restrict__ phiT, double *__restrict__ partials)
+{
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < dm.N; i += (int64_t)gridDim.x * blockDim.x)
+        acc += c_ln<double>((double)phiT[(size_t)tokens[i] * dm.Ks + z[i]] + 1e-12);
+    double t = block_sum(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+cudaError_t launch_lp_tokens(const Dims &dm, const int32_t *tokens, const int32_t *z,
+                             const float *phiT, double *partials, int n_partials, cudaStream_t st)
+{
+    lp_tokens_kernel<<<n_partials, RED_THREADS, 0, st>>>(dm, tokens, z, phiT, partials);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+lp_theta_kernel(Dims dm, const int64_t *__restrict__ doc_off, const int32_t *__restrict__ z,
+                const float *__restrict__ theta, const double *__restrict__ alpha, double *__restrict__ partials)
+{
+    extern __shared__ int32_t s_cnt[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    int32_t *cnt = s_cnt + (size_t)warp * dm.Ks;
+    for (int i = lane; i < dm.Ks; i += 32) cnt[i] = 0;
+    __syncwarp();
+    double acc = 0.0;
+    for (int64_t d = (int64_t)blockIdx.x * nwarp + warp; d < dm.D; d += (int64_t)gridDim.x * nwarp) {
+        for (int64_t t = doc_off[d] + lane; t < doc_off[d + 1]; t += 32) atomicAdd(&cnt[z[t]], 1);
+        __syncwarp();
+        const float *trow = theta + (size_t)d * dm.Ks;
+        for (int k = lane; k < dm.K; k += 32) {
+            acc += ((double)cnt[k] + alpha[k] - 1.0) * c_ln<double>((double)trow[k] + 1e-12);
+            cnt[k] = 0;
+        }
+        __syncwarp();
+    }
+    double t = block_sum(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+cudaError_t launch_lp_theta(const Dims &dm, const int64_t *doc_off, const int32_t *z,
+                            const float *theta, const double *alpha, double *partials,
+                            int n_partials, int sm_count, cudaStream_t st)
+{
+    (void)sm_count;
+    size_t smem = sizeof(int32_t) * (size_t)dm.Ks * (RED_THREADS / 32);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(lp_theta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    lp_theta_kernel<<<n_partials, RED_THREADS, smem, st>>>(dm, doc_off, z, theta, alpha, partials);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+lp_phi_kernel(Dims dm, const float *__restrict__ phiT, double beta, int32_t row0, int32_t row1,
+              double *__restrict__ partials)
+{
+    double acc = 0.0;
+    const int64_t cells = (int64_t)(row1 - row0) * dm.Ks;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t w = row0 + (int32_t)(i / dm.Ks);
+        const int k = (int)(i % dm.Ks);
+        if (w >= dm.V || k >= dm.K) continue;
+        acc += c_ln<double>((double)phiT[(size_t)w * dm.Ks + k] + 1e-12);
+    }
+    double t = block_sum(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = (beta - 1.0) * t;
+}
+cudaError_t launch_lp_phi(const Dims &dm, const float *phiT, double beta, int32_t row0, int32_t row1,
+                          double *partials, int n_partials, cudaStream_t st)
+{
+    lp_phi_kernel<<<n_partials, RED_THREADS, 0, st>>>(dm, phiT, beta, row0, row1, partials);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// accessors: layout conversion between the device layout and the reference's Java arrays
+// ---------------------------------------------------------------------------------------
+__global__ void export_phi_kernel(Dims dm, const float *__restrict__ phiT, double *__restrict__ out)
+{
+    // tile transpose [V][Ks] -> [K][V]
+    __shared__ float tile[32][33];
+    const int w0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int w = w0 + r, k = k0 + threadIdx.x;
+        tile[r][threadIdx.x] = (w < dm.V && k < dm.K) ? phiT[(size_t)w * dm.Ks + k] : 0.0f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int k = k0 + r, w = w0 + threadIdx.x;
+        if (k < dm.K && w < dm.V) out[(size_t)k * dm.V + w] = (double)tile[threadIdx.x][r];
+    }
+}
+cudaError_t launch_export_phi(const Dims &dm, const float *phiT, double *phi_kv, cudaStream_t st)
+{
+    dim3 grid((dm.V + 31) / 32, (dm.K + 31) / 32), block(32, 8);
+    export_phi_kernel<<<grid, block, 0, st>>>(dm, phiT, phi_kv);
+    return cudaGetLastError();
+}
+
+__global__ void import_phi_kernel(Dims dm, const double *__restrict__ in, float *__restrict__ phiT)
+{
+    __shared__ float tile[32][33];
+    const int w0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int k = k0 + r, w = w0 + threadIdx.x;
+        tile[r][threadIdx.x] = (w < dm.V && k < dm.K) ? (float)in[(size_t)k * dm.V + w] : 0.0f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int w = w0 + r, k = k0 + threadIdx.x;
+        if (w < dm.V && k < dm.K) phiT[(size_t)w * dm.Ks + k] = tile[threadIdx.x][r];
+    }
+}
+cudaError_t launch_import_phi(const Dims &dm, const double *phi_kv, float *phiT, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(phiT, 0, sizeof(float) * (size_t)dm.Vp * dm.Ks, st);
+    if (e != cudaSuccess) return e;
+    dim3 grid((dm.V + 31) / 32, (dm.K + 31) / 32), block(32, 8);
+    import_phi_kernel<<<grid, block, 0, st>>>(dm, phi_kv, phiT);
+    return cudaGetLastError();
+}
+
+__global__ void export_mean_kernel(Dims dm, const double *__restrict__ sum_vk, double scale, double *__restrict__ out)
+{
+    __shared__ double tile[32][33];
+    const int w0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int w = w0 + r, k = k0 + threadIdx.x;
+        tile[r][threadIdx.x] = (w < dm.V && k < dm.K) ? sum_vk[(size_t)w * dm.Ks + k] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int k = k0 + r, w = w0 + threadIdx.x;
+        if (k < dm.K && w < dm.V) out[(size_t)k * dm.V + w] = tile[threadIdx.x][r] * scale;
+    }
+}
+cudaError_t launch_export_mean(const Dims &dm, const double *sum_vk, double scale, double *out_kv, cudaStream_t st)
+{
+    dim3 grid((dm.V + 31) / 32, (dm.K + 31) / 32), block(32, 8);
+    export_mean_kernel<<<grid, block, 0, st>>>(dm, sum_vk, scale, out_kv);
+    return cudaGetLastError();
+}
+
+__global__ void export_counts_kernel(Dims dm, const int32_t *__restrict__ n_wk, int32_t *__restrict__ out)
+{
+    const int64_t cells = (int64_t)dm.V * dm.K;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = n_wk[(size_t)(i / dm.K) * dm.Ks + (i % dm.K)];
+}
+cudaError_t launch_export_counts(const Dims &dm, const int32_t *n_wk, int32_t *out_vk, cudaStream_t st)
+{
+    int64_t cells = (int64_t)dm.V * dm.K;
+    int64_t grid = (cells + 255) / 256;
+    if (grid > 65535) grid = 65535;
+    export_counts_kernel<<<(unsigned)grid, 256, 0, st>>>(dm, n_wk, out_vk);
+    return cudaGetLastError();
+}
+
+__global__ void export_theta_kernel(Dims dm, const float *__restrict__ theta, double *__restrict__ out)
+{
+    const int64_t cells = dm.D * dm.K;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (double)theta[(size_t)(i / dm.K) * dm.Ks + (i % dm.K)];
+}
+cudaError_t launch_export_theta(const Dims &dm, const float *theta, double *out, cudaStream_t st)
+{
+    int64_t cells = dm.D * dm.K;
+    if (cells == 0) return cudaSuccess;
+    int64_t grid = (cells + 255) / 256;
+    if (grid > 65535) grid = 65535;
+    export_theta_kernel<<<(unsigned)grid, 256, 0, st>>>(dm, theta, out);
+    return cudaGetLastError();
+}
+__global__ void import_theta_kernel(Dims dm, const double *__restrict__ in, float *__restrict__ theta)
+{
+    const int64_t cells = dm.D * dm.Ks;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t d = i / dm.Ks;
+        int k = (int)(i % dm.Ks);
+        theta[i] = k < dm.K ? (float)in[(size_t)d * dm.K + k] : 0.0f;
+    }
+}
+cudaError_t launch_import_theta(const Dims &dm, const double *in, float *theta, cudaStream_t st)
+{
+    int64_t cells = dm.D * dm.Ks;
+    if (cells == 0) return cudaSuccess;
+    int64_t grid = (cells + 255) / 256;
+    if (grid > 65535) grid = 65535;
+    import_theta_kernel<<<(unsigned)grid, 256, 0, st>>>(dm, in, theta);
+    return cudaGetLastError();
+}
+
+}  // namespace ldagpu

@@ -1,0 +1,412 @@
+// kernels_z.cu -- K1: the z-step of one Gibbs sweep, and the GGS theta draw that feeds it.
+//
+// Replaces (reference, src/main/java/cc/mallet/topics/):
+//   LDAGroupedGibbsSampler.java:47-132      GGS  z-step (theta draw :60-72, token loop :79-130)
+//   UncollapsedParallelLDA.java:1466-1545   PCGS z-step
+//   UncollapsedParallelLDA.java:1354-1437   RecursiveDocumentSampler / loopOverBatches (scheduling)
+//
+// Design: one warp owns one work item (GGS: a chunk of <= 256 tokens of one
+// document; PCGS: one whole document, because n_dk changes token by token).  The K topics of a
+// token are spread over the lanes, lane l owning topics 4l..4l+3 of every 128-topic tile, so one
+// Phi^T row is read as coalesced float4.  Rows are fetched by the TMA engine (cp.async.bulk,
+// 1-D) into a per-warp shared-memory ring, a few rows ahead of the consumer.  A run of equal
+// word types shares one row fetch (and, for GGS, one prefix scan).  The categorical draw is a
+// fixed three-level fp32 prefix tree (lane-local prefix, Kogge-Stone warp scan, sequential tile
+// bases) so the CPU oracle can reproduce the sampled topic bit for bit; uniforms are
+// Philox4x32-10 keyed by the global token index.
+#include "common.cuh"
+#include "contract_math.cuh"
+
+namespace ldagpu {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int Z_WARPS = 8;    // warps per CTA
+constexpr int Z_STAGES = 3;   // Phi^T rows in flight per warp
+
+template <int NT> struct RowScan {
+    float p[NT][4];   // lane-local inclusive prefix of the 4 owned scores, per tile
+    float incl[NT];   // inclusive warp scan of the lane totals, per tile
+    float B[NT];      // inclusive cumulative tile totals (warp-uniform)
+};
+
+template <int NT>
+__device__ __forceinline__ void scan_scores(const float4 (&a)[NT], const float4 (&ph)[NT],
+                                            RowScan<NT> &rs, int lane)
+{
+    float base = 0.0f;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        float p0 = __fmul_rn(a[j].x, ph[j].x);
+        float p1 = __fadd_rn(p0, __fmul_rn(a[j].y, ph[j].y));
+        float p2 = __fadd_rn(p1, __fmul_rn(a[j].z, ph[j].z));
+        float p3 = __fadd_rn(p2, __fmul_rn(a[j].w, ph[j].w));
+        rs.p[j][0] = p0; rs.p[j][1] = p1; rs.p[j][2] = p2; rs.p[j][3] = p3;
+        float x = p3;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            float y = __shfl_up_sync(FULL, x, off);
+            if (lane >= off) x = __fadd_rn(x, y);
+        }
+        rs.incl[j] = x;
+        base = __fadd_rn(base, __shfl_sync(FULL, x, 31));
+        rs.B[j] = base;
+    }
+}
+
+// first k with cumsum_k >= U * sum, searched tile -> lane -> element
+template <int NT>
+__device__ __forceinline__ int draw_topic(const RowScan<NT> &rs, float U, int lane, int K)
+{
+    float u = __fmul_rn(U, rs.B[NT - 1]);
+    int js = NT - 1;
+#pragma unroll
+    for (int j = NT - 2; j >= 0; --j)
+        if (rs.B[j] >= u) js = j;
+    float base = 0.0f, inc = rs.incl[0];
+    float q0 = rs.p[0][0], q1 = rs.p[0][1], q2 = rs.p[0][2];
+#pragma unroll
+    for (int j = 1; j < NT; ++j)
+        if (js == j) {
+            base = rs.B[j - 1]; inc = rs.incl[j];
+            q0 = rs.p[j][0]; q1 = rs.p[j][1]; q2 = rs.p[j][2];
+        }
+    float r = __fsub_rn(u, base);
+    unsigned m = __ballot_sync(FULL, inc >= r);
+    int ls = m ? __ffs(m) - 1 : 31;
+    float prev = __shfl_up_sync(FULL, inc, 1);
+    if (lane == 0) prev = 0.0f;
+    float r2 = __fsub_rn(r, prev);
+    int i = 3;
+    if (q2 >= r2) i = 2;
+    if (q1 >= r2) i = 1;
+    if (q0 >= r2) i = 0;
+    int k = __shfl_sync(FULL, TILE * js + 4 * lane + i, ls);
+    return k < K ? k : K - 1;
+}
+
+// shared-memory footprint of one warp, in bytes
+template <int NT, bool PCGS> __host__ __device__ constexpr size_t z_warp_smem()
+{
+    return (size_t)Z_STAGES * NT * TILE * 4 + (PCGS ? (size_t)NT * TILE * 8 : 0);
+}
+template <int NT, bool PCGS> __host__ __device__ constexpr size_t z_cta_smem()
+{
+    return Z_WARPS * z_warp_smem<NT, PCGS>() + (PCGS ? (size_t)NT * TILE * 4 : 0) +
+           (size_t)Z_WARPS * Z_STAGES * 8;
+}
+
+template <int NT, bool PCGS>
+__global__ void __launch_bounds__(Z_WARPS * 32) z_kernel(ZArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int ROWF = NT * TILE;
+    unsigned char *wbase = smem_raw + (size_t)warp * z_warp_smem<NT, PCGS>();
+    float *ring = reinterpret_cast<float *>(wbase);
+    int *cnt = reinterpret_cast<int *>(wbase + (size_t)Z_STAGES * ROWF * 4);       // PCGS only
+    float *av = reinterpret_cast<float *>(wbase + (size_t)Z_STAGES * ROWF * 4 + (size_t)ROWF * 4);
+    float *alpha_s = reinterpret_cast<float *>(smem_raw + Z_WARPS * z_warp_smem<NT, PCGS>());
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + Z_WARPS * z_warp_smem<NT, PCGS>() +
+                                                  (PCGS ? (size_t)ROWF * 4 : 0)) + warp * Z_STAGES;
+    const int K = a.dm.K, Ks = a.dm.Ks;
+    const uint32_t row_bytes = (uint32_t)Ks * 4u;
+
+    // zero the ring once: the bulk copies only ever write the first Ks floats of a slot, so the
+    // padding topics read as +0 for the whole kernel
+    for (int i = lane; i < Z_STAGES * ROWF / 4; i += 32)
+        reinterpret_cast<float4 *>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (PCGS) {
+        for (int i = lane; i < ROWF / 4; i += 32) reinterpret_cast<int4 *>(cnt)[i] = make_int4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < ROWF; i += blockDim.x) alpha_s[i] = i < Ks ? a.alpha[i] : 0.0f;
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < Z_STAGES; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (PCGS) __syncthreads(); else __syncwarp();
+
+    uint32_t fill = 0, cons = 0;   // rows issued / consumed so far by this warp (warp-uniform)
+
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(a.work_counter, 1ull);
+        item = __shfl_sync(FULL, item, 0);
+        if ((int64_t)item >= a.n_items) break;
+
+        int64_t d, t0, t1;
+        float4 th[NT];
+        if (PCGS) {
+            d = a.item_doc[item];
+            t0 = a.doc_off[d];
+            t1 = a.doc_off[d + 1];
+            if (t0 == t1) continue;   // UncollapsedParallelLDA.java:1474
+            for (int64_t t = t0 + lane; t < t1; t += 32) atomicAdd(&cnt[a.z[t]], 1);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                int4 c = reinterpret_cast<const int4 *>(cnt)[j * 32 + lane];
+                float4 al = reinterpret_cast<const float4 *>(alpha_s)[j * 32 + lane];
+                float4 v;
+                v.x = __fadd_rn(__int2float_rn(c.x), al.x);
+                v.y = __fadd_rn(__int2float_rn(c.y), al.y);
+                v.z = __fadd_rn(__int2float_rn(c.z), al.z);
+                v.w = __fadd_rn(__int2float_rn(c.w), al.w);
+                reinterpret_cast<float4 *>(av)[j * 32 + lane] = v;
+            }
+            __syncwarp();
+        } else {
+            d = a.item_doc[item];
+            t0 = a.item_begin[item];
+            int64_t de = a.doc_off[d + 1];
+            t1 = t0 + GGS_CHUNK < de ? t0 + GGS_CHUNK : de;
+            const float *trow = a.theta + (size_t)d * Ks;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                int k0 = j * TILE + lane * 4;
+                th[j] = k0 < Ks ? __ldg(reinterpret_cast<const float4 *>(trow + k0))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+
+        for (int64_t tb = t0; tb < t1; tb += 32) {
+            const int64_t t = tb + lane;
+            const bool valid = t < t1;
+            const int nvalid = (int)((t1 - tb) < 32 ? (t1 - tb) : 32);
+            int w = valid ? a.tokens[t] : -1;
+            int zold = (PCGS && valid) ? a.z[t] : 0;
+            int wprev = __shfl_up_sync(FULL, w, 1);
+            unsigned heads = __ballot_sync(FULL, valid && (lane == 0 || w != wprev));
+            float U = 0.0f;
+            if (valid) {
+                unsigned long long gt = (unsigned long long)(a.dm.token_base + t);
+                uint4 r = philox4x32_10((uint32_t)gt, (uint32_t)(gt >> 32), a.sweep, STREAM_Z << 24,
+                                        a.seed_lo, a.seed_hi);
+                U = uniform23(r.x);
+            }
+            int znew = 0;
+            unsigned pending = heads;   // run heads whose row has not been requested yet
+
+            // producer: keep up to Z_STAGES row fetches in flight
+            auto produce = [&]() {
+                while (pending && fill - cons < (uint32_t)Z_STAGES) {
+                    int b = __ffs(pending) - 1;
+                    pending &= pending - 1;
+                    int wrow = __shfl_sync(FULL, w, b);
+                    if (lane == 0) {
+                        uint32_t slot = fill % Z_STAGES;
+                        mbar_expect_tx(&bars[slot], row_bytes);
+                        bulk_g2s(ring + (size_t)slot * ROWF, a.phiT + (size_t)wrow * Ks, row_bytes, &bars[slot]);
+                    }
+                    ++fill;
+                }
+            };
+            produce();
+
+            unsigned rem = heads;
+            while (rem) {
+                const int b = __ffs(rem) - 1;
+                rem &= rem - 1;
+                const int e = rem ? __ffs(rem) - 1 : nvalid;   // run = tokens [b, e) of this block
+                const uint32_t slot = cons % Z_STAGES;
+                mbar_wait(&bars[slot], (cons / Z_STAGES) & 1u);
+                float4 ph[NT];
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+                    ph[j] = reinterpret_cast<const float4 *>(ring + (size_t)slot * ROWF)[j * 32 + lane];
+                __syncwarp();
+                ++cons;
+                produce();   // the slot is free again: request the next row while we compute
+
+                RowScan<NT> rs;
+                if (!PCGS) scan_scores<NT>(th, ph, rs, lane);
+                for (int tt = b; tt < e; ++tt) {
+                    if (PCGS) {
+                        // remove the token from the document counts (UncollapsedParallelLDA.java:1494)
+                        int old = __shfl_sync(FULL, zold, tt);
+                        if (lane == 0) {
+                            int c = cnt[old] - 1;
+                            cnt[old] = c;
+                            av[old] = __fadd_rn(__int2float_rn(c), alpha_s[old]);
+                        }
+                        __syncwarp();
+                        float4 aa[NT];
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) aa[j] = reinterpret_cast<const float4 *>(av)[j * 32 + lane];
+                        scan_scores<NT>(aa, ph, rs, lane);
+                    }
+                    float Ut = __shfl_sync(FULL, U, tt);
+                    int k = draw_topic<NT>(rs, Ut, lane, K);
+                    if (lane == tt) znew = k;
+                    if (PCGS) {
+                        // add it back under its new topic (UncollapsedParallelLDA.java:1535)
+                        if (lane == 0) {
+                            int c = cnt[k] + 1;
+                            cnt[k] = c;
+                            av[k] = __fadd_rn(__int2float_rn(c), alpha_s[k]);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            if (valid) a.z[t] = znew;
+        }
+        if (PCGS) {
+            // leave the histogram clean for the next document
+            for (int i = lane; i < ROWF / 4; i += 32) reinterpret_cast<int4 *>(cnt)[i] = make_int4(0, 0, 0, 0);
+            __syncwarp();
+        }
+    }
+}
+
+template <int NT, bool PCGS>
+static cudaError_t launch_z_t(const ZArgs &a, int sm_count, cudaStream_t st)
+{
+    constexpr size_t smem = z_cta_smem<NT, PCGS>();
+    static bool configured = false;
+    static int ctas_per_sm = 1;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(z_kernel<NT, PCGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, z_kernel<NT, PCGS>, Z_WARPS * 32, smem);
+        if (e != cudaSuccess) return e;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        configured = true;
+    }
+    int64_t warps_needed = a.n_items;
+    int64_t grid = (int64_t)sm_count * ctas_per_sm;   // persistent: every resident warp pulls items
+    int64_t need = (warps_needed + Z_WARPS - 1) / Z_WARPS;
+    if (need < grid) grid = need;
+    if (grid < 1) grid = 1;
+    z_kernel<NT, PCGS><<<(unsigned)grid, Z_WARPS * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <bool PCGS> static cudaError_t launch_z_any(const ZArgs &a, int sm_count, cudaStream_t st)
+{
+    if (a.n_items == 0) return cudaSuccess;
+    int nt = a.dm.NT;
+    if (nt <= 1) return launch_z_t<1, PCGS>(a, sm_count, st);
+    if (nt <= 2) return launch_z_t<2, PCGS>(a, sm_count, st);
+    if (nt <= 4) return launch_z_t<4, PCGS>(a, sm_count, st);
+    if (nt <= 8) return launch_z_t<8, PCGS>(a, sm_count, st);
+    return cudaErrorInvalidValue;   // K > 1024: dense register path not built
+}
+
+cudaError_t launch_z_ggs(const ZArgs &a, int sm_count, cudaStream_t st) { return launch_z_any<false>(a, sm_count, st); }
+cudaError_t launch_z_pcgs(const ZArgs &a, int sm_count, cudaStream_t st) { return launch_z_any<true>(a, sm_count, st); }
+
+// ---------------------------------------------------------------------------------------
+// GGS theta draw: theta_d ~ Dir(n_d + alpha) from the counts before the document is resampled
+// (LDAGroupedGibbsSampler.java:60-72; ParallelDirichlet.java:46-70 = K Gammas, normalise, floor).
+// One warp per document.  Each lane walks its own 4*NT cells with a flattened attempt loop, so
+// lanes do not wait for each other's rejections; the normalising sum follows the lane/tile order
+// of the contract (lane-sequential, then xor butterfly).
+// ---------------------------------------------------------------------------------------
+constexpr int TH_WARPS = 8;
+
+__global__ void __launch_bounds__(TH_WARPS * 32) theta_kernel(ThetaArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int NT = a.dm.NT, K = a.dm.K, Ks = a.dm.Ks;
+    const int ROWF = NT * TILE;
+    int *cnt = reinterpret_cast<int *>(smem_raw) + (size_t)warp * ROWF;
+    float *g = reinterpret_cast<float *>(smem_raw + (size_t)TH_WARPS * ROWF * 4) + (size_t)warp * ROWF;
+    for (int i = lane; i < ROWF; i += 32) cnt[i] = 0;
+    __syncwarp();
+
+    for (;;) {
+        unsigned long long dd = 0;
+        if (lane == 0) dd = atomicAdd(a.work_counter, 1ull);
+        dd = __shfl_sync(FULL, dd, 0);
+        if ((int64_t)dd >= a.dm.D) break;
+        const int64_t d = (int64_t)dd;
+        const int64_t t0 = a.doc_off[d], t1 = a.doc_off[d + 1];
+        float *trow = a.theta + (size_t)d * Ks;
+        if (t0 == t1) {   // empty document: the reference skips it, its theta row stays zero
+            for (int i = lane; i < Ks; i += 32) trow[i] = 0.0f;
+            continue;
+        }
+        for (int64_t t = t0 + lane; t < t1; t += 32) atomicAdd(&cnt[a.z[t]], 1);
+        __syncwarp();
+
+        const unsigned long long cell0 = (unsigned long long)(a.dm.doc_base + d) * (unsigned long long)K;
+        const int ncell = NT * 4;
+        int q = 0;
+        uint32_t attempt = 0;
+        float acc = 0.0f, shape = 0.f, dd_ = 0.f, cc_ = 0.f;
+        bool boost = false, fresh = true;
+        int k = lane * 4;
+        while (q < ncell) {
+            if (fresh) {
+                k = (q >> 2) * TILE + lane * 4 + (q & 3);
+                if (k >= K) { g[k] = 0.0f; ++q; continue; }
+                shape = __fadd_rn(__int2float_rn(cnt[k]), a.alpha[k]);
+                gamma_setup<float>(shape, boost, dd_, cc_);
+                attempt = 0;
+                fresh = false;
+            }
+            unsigned long long cell = cell0 + (unsigned long long)k;
+            uint4 w = philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), a.sweep,
+                                    (STREAM_THETA << 24) | attempt, a.seed_lo, a.seed_hi);
+            float gv;
+            if (gamma_attempt<float>(shape, boost, dd_, cc_, w, gv)) {
+                g[k] = gv;
+                acc = __fadd_rn(acc, gv);
+                ++q;
+                fresh = true;
+            } else {
+                ++attempt;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, off));
+        const float sum = acc;
+        for (int j = 0; j < NT; ++j) {
+            int k0 = j * TILE + lane * 4;
+            float4 v = reinterpret_cast<const float4 *>(g)[j * 32 + lane];
+            if (sum != 0.0f) {
+                v.x = __fdiv_rn(v.x, sum); v.y = __fdiv_rn(v.y, sum);
+                v.z = __fdiv_rn(v.z, sum); v.w = __fdiv_rn(v.w, sum);
+                if (v.x <= 0.0f) v.x = 0x1p-149f;
+                if (v.y <= 0.0f) v.y = 0x1p-149f;
+                if (v.z <= 0.0f) v.z = 0x1p-149f;
+                if (v.w <= 0.0f) v.w = 0x1p-149f;
+            }
+            // padding topics (k >= K) carry no probability
+            if (k0 + 0 >= K) v.x = 0.0f;
+            if (k0 + 1 >= K) v.y = 0.0f;
+            if (k0 + 2 >= K) v.z = 0.0f;
+            if (k0 + 3 >= K) v.w = 0.0f;
+            if (k0 < Ks) reinterpret_cast<float4 *>(trow)[k0 >> 2] = v;
+            reinterpret_cast<int4 *>(cnt)[j * 32 + lane] = make_int4(0, 0, 0, 0);
+        }
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_theta(const ThetaArgs &a, int sm_count, cudaStream_t st)
+{
+    if (a.dm.D == 0) return cudaSuccess;
+    size_t smem = (size_t)TH_WARPS * a.dm.NT * TILE * 8;
+    static size_t configured_smem = 0;
+    if (smem > configured_smem) {
+        cudaError_t e = cudaFuncSetAttribute(theta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured_smem = smem;
+    }
+    int per_sm = 1;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, theta_kernel, TH_WARPS * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)sm_count * per_sm;
+    int64_t need = (a.dm.D + TH_WARPS - 1) / TH_WARPS;
+    if (need < grid) grid = need;
+    theta_kernel<<<(unsigned)grid, TH_WARPS * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace ldagpu

@@ -1,0 +1,453 @@
+"""Host-side mirror of the reference's sampler interface over libldagpu.so.
+
+The reference picks a sampler by the ``scheme`` string (topics/tui/ParallelLDA.java:401-490); a sampler
+is any class implementing ``LDAGibbsSampler`` (topics/LDAGibbsSampler.java:10-47) and, for the
+Phi-based ones, ``LDASamplerWithPhi`` (topics/LDASamplerWithPhi.java:5-12).  ``GpuLDASampler`` keeps
+those method names, argument meanings and error behaviour for the two new schemes ``gpu_ggs`` and
+``gpu_pcgs``; every method is a thin call into the C ABI (include/ldagpu.h) -- the sweep itself runs
+inside the library.  The Java twin of this class is java/cc/mallet/topics/GpuLDASampler.java
+(INTEGRATION.md); there is no JDK in the build image, so Python carries the host side here.
+"""
+from __future__ import annotations
+
+import configparser
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import LdaGpuError, ptr
+from .corpus import InstanceList
+
+SCHEMES = {"gpu_ggs": 0, "gpu_pcgs": 1}
+
+
+@dataclass
+class LDAConfiguration:
+    """The configuration keys the hot path reads (configuration/LDAConfiguration.java:8-246,
+    configuration/ParsedLDAConfiguration.java:47-550); defaults as in LDAConfiguration.java:12-51."""
+
+    scheme: str = "gpu_ggs"
+    topics: int = 10                      # NO_TOPICS_DEFAULT
+    alpha: float = -1.0                   # < 0: ALPHA_DEFAULT = 50 / topics
+    beta: float = 0.01                    # BETA_DEFAULT
+    iterations: int = 200
+    seed: int = 0                         # 0 = clock in the reference (ParsedLDAConfiguration.java:137-141)
+    start_diagnostic: int = -1
+    compute_likelihood: bool = False
+    topic_interval: int = 10
+    save_phi_mean: bool = False           # the code reads save_phi_mean, the shipped cfgs write save_phi_means
+    phi_mean_burnin: int = 0              # percent of iterations (UPL:206-207)
+    phi_mean_thin: int = 1
+    exec_time: float = 10.0               # seconds of cumulative sampling time (LDAConfiguration.java:35)
+    dataset: Optional[str] = None
+    gpu_device: int = 0                   # new key
+
+    def getNoTopics(self, default: int = 10) -> int:
+        return self.topics
+
+    def getAlpha(self, default: float = 0.0) -> float:
+        return self.alpha if self.alpha > 0 else 50.0 / self.topics
+
+    def getBeta(self, default: float = 0.01) -> float:
+        return self.beta
+
+    def getNoIterations(self, default: int = 200) -> int:
+        return self.iterations
+
+    def getSeed(self, default: int = 0) -> int:
+        return self.seed
+
+    def getScheme(self) -> str:
+        return self.scheme
+
+    @staticmethod
+    def from_cfg(path: str, subconfig: Optional[str] = None, **overrides) -> "LDAConfiguration":
+        """Parse a reference .cfg: global keys, then the [subconfig] section wins
+        (configuration/SubConfig.java:57-67), then command-line style overrides
+        (configuration/LDACommandLineParser.java:45-64)."""
+        text = open(path, "r", encoding="utf-8").read()
+        cp = configparser.ConfigParser(inline_comment_prefixes=("#",), interpolation=None, strict=False)
+        cp.read_string("[__global__]\n" + text)
+        vals = dict(cp["__global__"])
+        if subconfig:
+            if subconfig not in cp:
+                raise KeyError(f"no sub-configuration [{subconfig}] in {path}")
+            vals.update(dict(cp[subconfig]))
+        vals.update({k: str(v) for k, v in overrides.items()})
+        c = LDAConfiguration()
+
+        def boolean(s):
+            return str(s).strip().lower() in ("true", "1", "yes")
+
+        for key, conv in (("scheme", str), ("topics", int), ("alpha", float), ("beta", float),
+                          ("iterations", int), ("seed", int), ("start_diagnostic", int),
+                          ("compute_likelihood", boolean), ("topic_interval", int),
+                          ("save_phi_mean", boolean), ("phi_mean_burnin", int), ("phi_mean_thin", int),
+                          ("exec_time", float), ("dataset", str), ("gpu_device", int)):
+            if key in vals:
+                setattr(c, key, conv(vals[key].strip()))
+        return c
+
+
+class GpuLDASampler:
+    """``LDAGibbsSampler`` + ``LDASamplerWithPhi`` for ``scheme = gpu_ggs | gpu_pcgs``."""
+
+    def __init__(self, config: LDAConfiguration, scheme: Optional[str] = None, device: Optional[int] = None):
+        self._L = _lib.load()
+        self.config = config
+        self.scheme = scheme or config.getScheme()
+        if self.scheme not in SCHEMES:
+            raise ValueError(f"unknown scheme {self.scheme!r}: expected one of {sorted(SCHEMES)}")
+        self.device = config.gpu_device if device is None else device
+        self.numTopics = config.getNoTopics()
+        a = config.getAlpha()
+        self.alpha = np.full(self.numTopics, a, np.float64)     # MSL:139-143 symmetric alpha
+        self.beta = float(config.getBeta())
+        self.startSeed = int(config.getSeed())
+        self._h = C.c_void_p()
+        self._data: Optional[InstanceList] = None
+        self._doc_off = None
+        self._tokens = None
+        self.loglikelihood: List[float] = []
+        self._rank, self._world = 0, 1
+        self._doc_base = self._token_base = 0
+
+    # ---- plumbing ---------------------------------------------------------------------------
+    def _ck(self, rc: int):
+        if rc:
+            msg = self._L.ldagpu_last_error(self._h if self._h else None)
+            raise LdaGpuError(msg.decode() if msg else "libldagpu error")
+
+    def _need(self):
+        if not self._h:
+            raise LdaGpuError("addInstances has not been called")
+
+    def close(self):
+        if self._h:
+            self._L.ldagpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- LDAGibbsSampler ---------------------------------------------------------------------
+    def setConfiguration(self, config: LDAConfiguration):
+        self.config = config
+
+    def getConfiguration(self) -> LDAConfiguration:
+        return self.config
+
+    def setRandomSeed(self, seed: int):
+        """MSL:153-156.  Also re-keys the in-sweep Philox stream when called before addInstances."""
+        self.startSeed = int(seed)
+
+    def getStartSeed(self) -> int:
+        return self.startSeed
+
+    def addInstances(self, training: InstanceList, *, rank: int = 0, world: int = 1,
+                     comm_id: Optional[bytes] = None, init_z: bool = True):
+        """UPL:357-456: upload the corpus, draw the initial z from java.util.Random(seed) in document
+        order (UPL:398-406), build the counts and draw the initial Phi (UPL:450).  With world > 1 this
+        rank keeps a token-balanced contiguous shard of the documents."""
+        from .corpus import shard_documents_by_tokens, take_shard
+        self.close()
+        self._data = training
+        off, tokens = training.to_csr()
+        self.numTypes = training.getNumTypes()
+        self._global_doc_off = off
+        if world > 1:
+            d0, d1 = shard_documents_by_tokens(off, world)[rank]
+            off, tokens, self._doc_base, self._token_base = take_shard(off, tokens, d0, d1)
+        self._doc_off, self._tokens = np.ascontiguousarray(off, np.int64), np.ascontiguousarray(tokens, np.int32)
+        self._rank, self._world = rank, world
+        self._ck(self._L.ldagpu_create(self.numTopics, self.numTypes, len(off) - 1, ptr(self._doc_off),
+                                       ptr(self._tokens) if len(tokens) else None, ptr(self.alpha), self.beta,
+                                       self.startSeed & 0xFFFFFFFFFFFFFFFF, SCHEMES[self.scheme], self.device,
+                                       self._doc_base, self._token_base, C.byref(self._h)))
+        if world > 1:
+            if comm_id is None:
+                raise ValueError("world > 1 needs the 128-byte communicator id (GpuLDASampler.make_comm_id on rank 0)")
+            buf = (C.c_char * 128).from_buffer_copy(comm_id)
+            self._ck(self._L.ldagpu_comm_init(self._h, rank, world, buf))
+        if init_z:
+            java_seed = ((self.startSeed + 2 ** 31) % 2 ** 32) - 2 ** 31     # Java int
+            self._ck(self._L.ldagpu_init_z_java_random(self._h, java_seed))
+        self.loglikelihood = []
+
+    @staticmethod
+    def make_comm_id() -> bytes:
+        buf = (C.c_char * 128)()
+        if _lib.load().ldagpu_comm_unique_id(buf):
+            raise LdaGpuError("ldagpu_comm_unique_id failed (is libnccl.so.2 loadable?)")
+        return bytes(buf)
+
+    def addTestInstances(self, testSet: InstanceList):
+        raise NotImplementedError("held-out evaluation (MarginalProbEstimatorPlain) is outside the GPU path")
+
+    def sample(self, iterations: int):
+        """UPL:552-943: `iterations` sweeps; log-likelihood every topic_interval sweeps when
+        compute_likelihood is set (UPL:587-593,838-853)."""
+        self._need()
+        cfg = self.config
+        if cfg.save_phi_mean:
+            burn = int(cfg.phi_mean_burnin / 100.0 * iterations)          # UPL:206-207
+            self._ck(self._L.ldagpu_set_phi_mean_schedule(self._h, burn, cfg.phi_mean_thin))
+        self.preSample()
+        if cfg.compute_likelihood:
+            self.loglikelihood.append(self.modelLogLikelihood())
+        hooked = any(getattr(type(self), n) is not getattr(GpuLDASampler, n)
+                     for n in ("preIteration", "postIteration", "preZ", "postZ", "prePhi", "postPhi"))
+        step = max(1, cfg.topic_interval) if cfg.compute_likelihood else iterations
+        done_total = 0
+        while done_total < iterations and not self.getAbort():
+            n = min(step, iterations - done_total)
+            if hooked:
+                for _ in range(n):
+                    self._one_hooked_sweep()
+                done = n
+            else:
+                d = C.c_int32(0)
+                self._ck(self._L.ldagpu_sweep(self._h, n, C.byref(d)))
+                done = d.value
+            done_total += done
+            if cfg.compute_likelihood and done == n and done_total % max(1, cfg.topic_interval) == 0:
+                self.loglikelihood.append(self.modelLogLikelihood())
+            if done < n:
+                break
+            z_ms, c_ms, p_ms, _ = self.getTimers()
+            if (z_ms + c_ms + p_ms) / 1000.0 >= cfg.exec_time > 0:        # UPL:926-928
+                break
+        self.postSample()
+
+    def _one_hooked_sweep(self):
+        L, h = self._L, self._h
+        self._ck(L.ldagpu_next_iteration(h))
+        self.preIteration()
+        self.preZ()
+        if self.scheme == "gpu_ggs":
+            self._ck(L.ldagpu_sample_theta(h))
+        self._ck(L.ldagpu_sample_z(h))
+        self._ck(L.ldagpu_rebuild_counts(h))
+        self.postZ()
+        self.prePhi()
+        self._ck(L.ldagpu_sample_phi(h))
+        self.postPhi()
+        self.postIteration()
+
+    def sampleZGivenPhi(self, iterations: int):
+        """LSWP:11, UPL:975-1014: z-only sweeps with Phi frozen."""
+        self._need()
+        d = C.c_int32(0)
+        self._ck(self._L.ldagpu_sample_z_given_phi(self._h, iterations, C.byref(d)))
+
+    def getNoTopics(self) -> int:
+        return self.numTopics
+
+    getNumTopics = getNoTopics
+
+    def getNoTypes(self) -> int:
+        return self.numTypes
+
+    def getCurrentIteration(self) -> int:
+        self._need()
+        it = C.c_int32(0)
+        self._ck(self._L.ldagpu_get_iteration(self._h, C.byref(it)))
+        return it.value
+
+    def get_z_flat(self) -> np.ndarray:
+        self._need()
+        z = np.zeros(len(self._tokens), np.int32)
+        self._ck(self._L.ldagpu_get_z(self._h, ptr(z)))
+        return z
+
+    def set_z_flat(self, z: np.ndarray, redraw_phi: bool = True):
+        self._need()
+        z = np.ascontiguousarray(z, np.int32)
+        if len(z) != len(self._tokens):
+            # UPL:1828-1830
+            raise ValueError(f"Count does not sum to nr. types! Sumtotal: {len(z)} no.types: {len(self._tokens)}")
+        self._ck(self._L.ldagpu_set_z(self._h, ptr(z), 1 if redraw_phi else 0))
+
+    def getZIndicators(self) -> List[np.ndarray]:
+        """MSL:464-477: int[D][] (local documents)."""
+        z, off = self.get_z_flat(), self._doc_off
+        return [z[off[d]: off[d + 1]].copy() for d in range(len(off) - 1)]
+
+    def setZIndicators(self, zIndicators: Sequence[Sequence[int]]):
+        """UPL:1797-1843: replace z, rebuild the counts, redraw Phi."""
+        flat = (np.concatenate([np.asarray(d, np.int32) for d in zIndicators])
+                if len(zIndicators) else np.zeros(0, np.int32))
+        lens = np.fromiter((len(d) for d in zIndicators), np.int64, len(zIndicators))
+        if len(lens) != len(self._doc_off) - 1 or np.any(lens != np.diff(self._doc_off)):
+            raise ValueError("zIndicators do not match the document lengths")
+        self.set_z_flat(flat, True)
+
+    def getDocumentTopicMatrix(self) -> np.ndarray:
+        """MSL:536-547: int[D][K]."""
+        self._need()
+        out = np.zeros((len(self._doc_off) - 1, self.numTopics), np.int32)
+        self._ck(self._L.ldagpu_get_doc_topic_counts(self._h, ptr(out)))
+        return out
+
+    def getZbar(self) -> np.ndarray:
+        """MSL:620-668: n_dk / N_d (zero rows for empty documents)."""
+        ndk = self.getDocumentTopicMatrix().astype(np.float64)
+        lens = np.diff(self._doc_off).astype(np.float64)
+        return np.divide(ndk, lens[:, None], out=np.zeros_like(ndk), where=lens[:, None] > 0)
+
+    def getThetaEstimate(self) -> np.ndarray:
+        """MSL:709-753: (n_dk + alpha_k) / sum_k (n_dk + alpha_k)."""
+        p = self.getDocumentTopicMatrix().astype(np.float64) + self.alpha[None, :]
+        return p / p.sum(axis=1, keepdims=True)
+
+    def getTypeTopicMatrix(self) -> np.ndarray:
+        """LGS:32 / UPL:226-234: int[V][K]."""
+        self._need()
+        out = np.zeros((self.numTypes, self.numTopics), np.int32)
+        self._ck(self._L.ldagpu_get_type_topic_counts(self._h, ptr(out)))
+        return out
+
+    getTypeTopicCounts = getTypeTopicMatrix
+
+    def getTopicTotals(self) -> np.ndarray:
+        """MSL:971-976: int[K]."""
+        self._need()
+        out = np.zeros(self.numTopics, np.int32)
+        self._ck(self._L.ldagpu_get_topic_totals(self._h, ptr(out)))
+        return out
+
+    def getDeltaStatistics(self):
+        raise NotImplementedError("per-sweep deltas are only read by the random-scan builders (SURVEY App. A)")
+
+    def getBeta(self) -> float:
+        return self.beta
+
+    def getAlpha(self) -> np.ndarray:
+        return self.alpha
+
+    def getDataset(self) -> InstanceList:
+        return self._data
+
+    def getAlphabet(self):
+        return self._data.getDataAlphabet()
+
+    def getCorpusSize(self) -> int:
+        return int(self._global_doc_off[-1])
+
+    def getTypeFrequencies(self) -> np.ndarray:
+        return np.bincount(self._tokens, minlength=self.numTypes).astype(np.int32)
+
+    def getTopTypeFrequencyIndices(self) -> np.ndarray:
+        return np.argsort(-self.getTypeFrequencies(), kind="stable").astype(np.int32)
+
+    def getTypeMassCumSum(self) -> np.ndarray:
+        f = self.getTypeFrequencies()[self.getTopTypeFrequencyIndices()].astype(np.float64)
+        return np.cumsum(f / max(f.sum(), 1.0))
+
+    def getLogLikelihood(self) -> List[float]:
+        return list(self.loglikelihood)
+
+    def getHeldOutLogLikelihood(self) -> List[float]:
+        return []
+
+    def modelLogLikelihood(self) -> float:
+        """UPL:1644-1758."""
+        self._need()
+        v = C.c_double(0)
+        self._ck(self._L.ldagpu_log_likelihood(self._h, C.byref(v)))
+        return v.value
+
+    def computeLogPosterior(self) -> float:
+        """UPL:1573-1634 (GGS: with the sweep's own theta, UPL:716-720)."""
+        self._need()
+        v = C.c_double(0)
+        self._ck(self._L.ldagpu_log_posterior(self._h, C.byref(v)))
+        return v.value
+
+    # hooks (MSL:783-810): no-ops; subclasses override, sample() then runs step-wise
+    def preSample(self): pass
+    def postSample(self): pass
+    def preIteration(self): pass
+    def postIteration(self): pass
+    def preZ(self): pass
+    def postZ(self): pass
+    def prePhi(self): pass
+    def postPhi(self): pass
+
+    # ---- AbortableSampler -------------------------------------------------------------------
+    def abort(self):
+        if self._h:
+            self._L.ldagpu_abort(self._h)
+
+    def getAbort(self) -> bool:
+        if not self._h:
+            return False
+        v = C.c_int32(0)
+        self._L.ldagpu_get_abort(self._h, C.byref(v))
+        return bool(v.value)
+
+    # ---- LDASamplerWithPhi -------------------------------------------------------------------
+    def getPhi(self) -> np.ndarray:
+        """UPL:1946-1948: double[K][V]."""
+        self._need()
+        out = np.zeros((self.numTopics, self.numTypes), np.float64)
+        self._ck(self._L.ldagpu_get_phi(self._h, ptr(out)))
+        return out
+
+    def setPhi(self, phi: np.ndarray, dataAlphabet=None, targetAlphabet=None):
+        """UPL:1897-1926."""
+        self._need()
+        if dataAlphabet is not None and self._data.alphabet.size() and not dataAlphabet == self.getAlphabet():
+            raise ValueError("Vocabularies does not match!")
+        phi = np.ascontiguousarray(phi, np.float64)
+        if phi.shape != (self.numTopics, self.numTypes):
+            raise ValueError(f"phi must be [{self.numTopics}][{self.numTypes}]")
+        self._ck(self._L.ldagpu_set_phi(self._h, ptr(phi)))
+
+    def getPhiMeans(self) -> Optional[np.ndarray]:
+        """UPL:1954-1966: None until a Phi has been accumulated."""
+        self._need()
+        out = np.zeros((self.numTopics, self.numTypes), np.float64)
+        n = C.c_int32(0)
+        self._ck(self._L.ldagpu_get_phi_mean(self._h, ptr(out), C.byref(n)))
+        return out if n.value > 0 else None
+
+    def getTheta(self) -> np.ndarray:
+        """thetaMatrix of the last sweep (UPL:78, GGS:72): double[D][K]."""
+        self._need()
+        out = np.zeros((len(self._doc_off) - 1, self.numTopics), np.float64)
+        self._ck(self._L.ldagpu_get_theta(self._h, ptr(out)))
+        return out
+
+    def setTheta(self, theta: np.ndarray):
+        self._need()
+        theta = np.ascontiguousarray(theta, np.float64)
+        self._ck(self._L.ldagpu_set_theta(self._h, ptr(theta)))
+
+    # ---- timers (the reference prints these, UPL:931-939) -----------------------------------
+    def getTimers(self):
+        v = [C.c_double(0) for _ in range(4)]
+        self._L.ldagpu_get_timers(self._h, *[C.byref(x) for x in v])
+        return tuple(x.value for x in v)
+
+    def getLastCallStats(self):
+        ms, zl, tl = C.c_double(0), C.c_int64(0), C.c_int64(0)
+        self._L.ldagpu_get_last_call_stats(self._h, C.byref(ms), C.byref(zl), C.byref(tl))
+        return ms.value, zl.value, tl.value
+
+    # step-wise access for tests
+    def _step(self, name: str):
+        self._need()
+        self._ck(getattr(self._L, "ldagpu_" + name)(self._h))
+
+
+def createModel(config: LDAConfiguration, scheme: Optional[str] = None) -> GpuLDASampler:
+    """The two new `case` labels of ParallelLDA.createModel (topics/tui/ParallelLDA.java:401-490)."""
+    return GpuLDASampler(config, scheme or config.getScheme())

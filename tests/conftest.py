@@ -1,0 +1,53 @@
+"""Shared fixtures.  Tests that need a GPU carry @pytest.mark.gpu; everything else runs on CPU.
+
+Only tests (and smoke / bench's cpu_baseline) may import the oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def make_corpus(D, V, mean_len, seed, sort_docs=True, empty_every=0, zipf=1.1):
+    """Small ragged corpus (numpy only): Zipf-ish types, Poisson lengths, optional empty documents."""
+    rng = np.random.default_rng(seed)
+    lens = rng.poisson(mean_len, D).astype(np.int64)
+    if empty_every:
+        lens[::empty_every] = 0
+    off = np.zeros(D + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    p = 1.0 / np.arange(1, V + 1) ** zipf
+    p /= p.sum()
+    tokens = rng.choice(V, size=int(off[-1]), p=p).astype(np.int32)
+    if sort_docs:
+        for d in range(D):
+            tokens[off[d]:off[d + 1]].sort()
+    return off, tokens
+
+
+@pytest.fixture(scope="session")
+def cats():
+    f = np.load(os.path.join(GOLDEN, "cats_corpus.npz"))
+    return f["doc_offsets"].astype(np.int64), f["tokens"].astype(np.int32)
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return np.load(os.path.join(GOLDEN, "oracle_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle as O
+    O.lib()
+    return O
