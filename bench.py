@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py -- token-topic samples/sec of one Gibbs sweep (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload pubmed8|nips|enron]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the CPU port of the reference's sampler, same metric
+
+A "step" is one full sweep ([theta] z, count rebuild, [exchange], Phi draw) over the rank's shard.
+Default workload: PubMed-shaped GGS, K=1000, V=141043, one eighth of the 8.2M-document corpus per GPU
+(weak scaling: at 8 GPUs it is exactly BASELINE.json configs[3]); Phi^T is 577 MB, larger than the
+126 MB L2, so no L2 flush is needed between steps.
+
+value   device-resident: K sweeps inside ONE ldagpu_sweep call, timed with CUDA events on the library's
+        stream, max over ranks.
+e2e     the same metric through the sampler API with host buffers: every step uploads z from pinned
+        host memory (setZIndicators path, keeps Phi), runs sample(1), reads z and the topic totals back.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # per-GPU shard; D scales with the number of GPUs (weak scaling)
+    "pubmed8": dict(desc="PubMed-shaped GGS K=1000, V=141043, per-GPU shard = 1/8 of the 8.2M-doc corpus",
+                    D=1025000, V=141043, mean_len=90.0, K=1000, scheme="gpu_ggs", alpha=0.05, beta=0.01),
+    "nips": dict(desc="NIPS-shaped GGS K=100 (BASELINE.json configs[1])",
+                 D=1500, V=12419, mean_len=1267.0, K=100, scheme="gpu_ggs", alpha=1.0, beta=0.01),
+    "enron": dict(desc="Enron-shaped PCGS K=400 (BASELINE.json configs[2])",
+                  D=39861, V=28102, mean_len=161.0, K=400, scheme="gpu_pcgs", alpha=0.125, beta=0.01),
+}
+METRIC = "token-topic samples/sec per Gibbs sweep"
+UNIT = "tokens/s"
+SEED = 2019
+CORPUS_SEED = 20190529
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_from_profiles(workload):
+    """dram bytes per z-kernel launch from the committed ncu capture, if there is one for this workload."""
+    p = os.path.join(ROOT, "profiles", "z_kernel_traffic.json")
+    if os.path.exists(p):
+        t = json.load(open(p)).get(workload)
+        if t:
+            return t.get("dram_bytes_per_launch")
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self, gpu_indices):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9 or not c[0].isdigit() or int(c[0]) not in gpu_indices:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(wl, off, tokens, budget_tokens, n_shard_tokens):
+    """The reference's sampler restated on the CPU (oracle, faithful mode, the reference's threading
+    shape) on a bounded sample: whole documents up to `budget_tokens` tokens, one sweep, all host
+    threads.  z cost is per token, Phi cost is per sweep (K*V Gammas, independent of the sample), so
+    the shard-level rate is N / (N * z_sec_per_token + phi_sec)."""
+    from oracle import oracle as O
+    d1 = int(np.searchsorted(off, budget_tokens, side="right")) - 1
+    d1 = max(1, min(d1, len(off) - 1))
+    o, t = off[: d1 + 1].copy(), tokens[: off[d1]].copy()
+    K, V = wl["K"], wl["V"]
+    z = O.java_next_ints(SEED, K, len(t))
+    sch = O.GGS if wl["scheme"] == "gpu_ggs" else O.PCGS
+    zs, ps, nt = O.baseline_sweeps(sch, o, t, z, V, K, np.full(K, wl["alpha"]), wl["beta"], SEED, 1)
+    per_tok = zs / max(len(t), 1)
+    value = n_shard_tokens / (n_shard_tokens * per_tok + ps)
+    return {"value": value, "unit": UNIT, "cores": nt, "kind": "port",
+            "sample": f"{d1} documents / {len(t)} tokens of the same corpus, 1 sweep: z+merge {zs:.3f}s "
+                      f"({per_tok * 1e9:.1f} ns/token), Phi draw {ps:.3f}s (full K*V); rate extrapolated to "
+                      f"the {n_shard_tokens}-token shard; no JDK in the image, so this is the C restatement "
+                      f"(oracle/lda_oracle.c oracle_baseline_sweeps), not the Java reference"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="pubmed8", choices=sorted(WORKLOADS))
+    ap.add_argument("--docs", type=int, default=0, help="override documents per GPU (debugging)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-tokens", type=int, default=3_000_000)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = dict(WORKLOADS[args.workload])
+    if args.docs:
+        wl["D"] = args.docs
+    config = {"workload": wl["desc"], "scheme": wl["scheme"], "K": wl["K"], "V": wl["V"],
+              "docs_per_gpu": wl["D"], "alpha": wl["alpha"], "beta": wl["beta"],
+              "l2": "inputs larger than L2 (Phi^T %.0f MB), no flush" % (wl["V"] * 4 * ((wl["K"] + 31) // 32 * 32) / 1e6)}
+
+    import ldagroupedgibbssampler_b200 as L
+
+    # ----------------------------------------------------------------------------------------
+    if args.impl == "reference":
+        # the reference's own CPU implementation of the path (C port; no JDK in the image), rank 0 only
+        if rank != 0:
+            return
+        off, tokens = L.synth_corpus(min(wl["D"], 60000), wl["V"], wl["mean_len"], seed=CORPUS_SEED)
+        n_shard = int(round(wl["D"] * wl["mean_len"])) * max(args.gpus, 1)
+        vals = []
+        for i in range(args.warmup + args.steps):
+            r = cpu_baseline(wl, off, tokens, args.cpu_sample_tokens // 3, n_shard)
+            if i >= args.warmup:
+                vals.append(r)
+        v = float(np.mean([x["value"] for x in vals]))
+        cb = dict(vals[-1]); cb["value"] = v
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": 1e3 * n_shard / v, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                          "cpu_baseline": cb,
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ----------------------------------------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+
+    if world > 1:
+        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+    torch.cuda.set_device(local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def all_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_sum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # this rank's shard of the global corpus (documents [rank*D, (rank+1)*D))
+    t0 = time.time()
+    off, tokens = L.synth_corpus(wl["D"], wl["V"], wl["mean_len"], seed=CORPUS_SEED, doc_first=rank * wl["D"])
+    n_local = len(tokens)
+    if world > 1:
+        sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([n_local], dtype=torch.int64, device="cuda"))
+        sizes = [int(s.item()) for s in sizes]
+    else:
+        sizes = [n_local]
+    token_base, n_total = sum(sizes[:rank]), sum(sizes)
+    gen_s = time.time() - t0
+
+    cfg = L.LDAConfiguration(scheme=wl["scheme"], topics=wl["K"], alpha=wl["alpha"], beta=wl["beta"], seed=SEED,
+                             exec_time=0)
+    s = L.GpuLDASampler(cfg, device=local_rank)
+    comm_id = None
+    if world > 1:
+        box = [L.GpuLDASampler.make_comm_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        comm_id = box[0]
+    s.addInstances(L.InstanceList.from_csr(off, tokens, wl["V"]), rank=rank, world=world, comm_id=comm_id,
+                   presharded=(rank * wl["D"], token_base, n_total))
+
+    # ---- device-resident: warm-up, then exactly K sweeps in one library call ---------------
+    s.sample(args.warmup)
+    clocks = ClockSampler()
+    barrier()
+    if rank == 0:
+        clocks.start()
+    w0 = time.perf_counter()
+    s.sample(args.steps)
+    barrier()
+    wall_ms = (time.perf_counter() - w0) * 1e3
+    call_ms, zk_ms, zk_launches, launches = s.getLastCallStats()
+    ck = clocks.stop(set(range(world))) if rank == 0 else None
+    dev_ms = all_max(call_ms)
+    wall_ms = all_max(wall_ms)
+    zk_ms_per_launch = all_max(zk_ms / max(zk_launches, 1))
+    value = n_total * args.steps / (dev_ms / 1e3)
+
+    # ---- end to end through the sampler API with pinned host buffers -----------------------
+    zbuf = torch.empty(max(n_local, 1), dtype=torch.int32, pin_memory=True)
+    znp = zbuf.numpy()[:n_local]
+    znp[:] = s.get_z_flat()
+    import ctypes as C
+    lib = L.load()
+
+    def e2e_step():
+        s._ck(lib.ldagpu_set_z(s._h, C.c_void_p(zbuf.data_ptr()), 0))        # H2D z (+ count rebuild, Phi kept)
+        s.sample(1)
+        s._ck(lib.ldagpu_get_z(s._h, C.c_void_p(zbuf.data_ptr())))           # D2H z
+        return s.getTopicTotals()                                           # D2H n_k
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_step()
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_ms = all_max((time.perf_counter() - e0) * 1e3)
+    e2e_value = n_total * args.steps / (e2e_ms / 1e3)
+
+    # ---- roofline of the dominant kernel (z-step) -------------------------------------------
+    peak, peak_src = peaks()
+    bytes_per_token = 4 * wl["K"] + 12                      # one fp32 K-vector + w + z in + z out
+    alg_bytes = bytes_per_token * max(sizes)                # one launch processes the rank's shard
+    achieved = alg_bytes / (zk_ms_per_launch / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "z_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_token": bytes_per_token,
+                "kernel_ms_per_launch": zk_ms_per_launch, "kernel_share_of_step": zk_ms / max(call_ms, 1e-9),
+                "traffic": traffic_from_profiles(args.workload)}
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": dict(config, tokens_total=n_total, tokens_per_gpu=sizes, corpus_gen_s=round(gen_s, 1),
+                          wall_ms_per_step=wall_ms / args.steps),
+           "clocks": ck,
+           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n_local,
+                   "d2h_bytes_per_step": 4 * n_local + 4 * wl["K"], "ms_per_step": e2e_ms / args.steps,
+                   "what": "per step: ldagpu_set_z from pinned host z, sample(1), ldagpu_get_z to pinned host, "
+                           "getTopicTotals; host wall clock, max over ranks"},
+           "gpu_launches": int(launches),
+           "roofline": roofline,
+           "timers_ms": dict(zip(("z", "counts", "phi", "comm"), s.getTimers()))}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(wl, off, tokens, args.cpu_sample_tokens, n_total)
+    s.close()
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

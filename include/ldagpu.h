@@ -118,17 +118,20 @@ int ldagpu_get_abort(ldagpu_handle h, int32_t *aborted);
 /* cumulative device time per phase in ms since creation (the reference's own timers:
  * zSamplingTimeCum = z + count merge, phiSamplingTimeCum; UPL:642-644,670-673,690-693,931-939) */
 int ldagpu_get_timers(ldagpu_handle h, double *z_ms, double *counts_ms, double *phi_ms, double *comm_ms);
-/* device time of the dominant kernel (the z-step launches) over the last ldagpu_sweep /
- * ldagpu_sample_z_given_phi call, and how many kernels that call launched */
-int ldagpu_get_last_call_stats(ldagpu_handle h, double *z_kernel_ms, int64_t *z_kernel_launches,
-                               int64_t *total_launches);
+/* over the last ldagpu_sweep / ldagpu_sample_z_given_phi call, measured with CUDA events on the
+ * library's stream: device time of the whole call, device time of the dominant kernel (the z-step
+ * launches), and how many kernels the call launched */
+int ldagpu_get_last_call_stats(ldagpu_handle h, double *call_ms, double *z_kernel_ms,
+                               int64_t *z_kernel_launches, int64_t *total_launches);
 
 /* host-side helper for benchmarks and tests: LDA-generative synthetic corpus of a given shape
  * (SURVEY 8d).  doc_offsets int64[D+1] out; tokens int32[capacity] out; returns N in *n_tokens.
- * Tokens of a document are sorted by type id (bag of words, like the bundled corpora). */
-int ldagpu_synth_corpus(int64_t D, int32_t V, int32_t K_gen, double mean_len, double sigma_len,
-                        int32_t max_len, uint64_t seed, int64_t *doc_offsets, int32_t *tokens,
-                        int64_t capacity, int64_t *n_tokens);
+ * Tokens of a document are sorted by type id (bag of words, like the bundled corpora).
+ * Generates documents [doc_first, doc_first + D) of the corpus that seed defines, so ranks can
+ * build their own shard. */
+int ldagpu_synth_corpus(int64_t D, int64_t doc_first, int32_t V, int32_t K_gen, double mean_len,
+                        double sigma_len, int32_t max_len, uint64_t seed, int64_t *doc_offsets,
+                        int32_t *tokens, int64_t capacity, int64_t *n_tokens);
 
 #ifdef __cplusplus
 }

@@ -74,8 +74,8 @@ def load() -> C.CDLL:
     sig("ldagpu_log_posterior", C.c_int, vp, pf64)
     sig("ldagpu_get_abort", C.c_int, vp, pi32)
     sig("ldagpu_get_timers", C.c_int, vp, pf64, pf64, pf64, pf64)
-    sig("ldagpu_get_last_call_stats", C.c_int, vp, pf64, pi64, pi64)
-    sig("ldagpu_synth_corpus", C.c_int, i64, i32, i32, f64, f64, i32, u64, vp, vp, i64, pi64)
+    sig("ldagpu_get_last_call_stats", C.c_int, vp, pf64, pf64, pi64, pi64)
+    sig("ldagpu_synth_corpus", C.c_int, i64, i64, i32, i32, f64, f64, i32, u64, vp, vp, i64, pi64)
     _lib = L
     return L
 
@@ -85,16 +85,16 @@ def ptr(a: np.ndarray):
 
 
 def synth_corpus(D: int, V: int, mean_len: float, seed: int = 20190529, K_gen: int = 50,
-                 sigma_len: float = 0.6, max_len: int = 20000):
+                 sigma_len: float = 0.6, max_len: int = 20000, doc_first: int = 0):
     """LDA-generative synthetic corpus of a given shape.  Returns (doc_offsets, tokens)."""
     L = load()
     off = np.zeros(D + 1, np.int64)
     n = C.c_int64(0)
-    rc = L.ldagpu_synth_corpus(D, V, K_gen, mean_len, sigma_len, max_len, seed, ptr(off), None, 0, C.byref(n))
+    rc = L.ldagpu_synth_corpus(D, doc_first, V, K_gen, mean_len, sigma_len, max_len, seed, ptr(off), None, 0, C.byref(n))
     if rc:
         raise LdaGpuError("ldagpu_synth_corpus (sizing) failed")
     tokens = np.zeros(max(n.value, 1), np.int32)
-    rc = L.ldagpu_synth_corpus(D, V, K_gen, mean_len, sigma_len, max_len, seed, ptr(off), ptr(tokens),
+    rc = L.ldagpu_synth_corpus(D, doc_first, V, K_gen, mean_len, sigma_len, max_len, seed, ptr(off), ptr(tokens),
                                n.value, C.byref(n))
     if rc:
         raise LdaGpuError("ldagpu_synth_corpus failed")

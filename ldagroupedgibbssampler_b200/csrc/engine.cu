@@ -142,7 +142,7 @@ struct ldagpu_handle_s {
     std::atomic<int> abort_flag{0};
     std::string err;
     double t_z = 0, t_counts = 0, t_phi = 0, t_comm = 0;
-    double last_zk_ms = 0;
+    double last_zk_ms = 0, last_call_ms = 0;
     int64_t last_zk_launches = 0, last_launches = 0;
 
     int fail(const char *fmt, ...)
@@ -289,7 +289,7 @@ int sync_check(ldagpu_handle h)
 
 int run_sweeps(ldagpu_handle h, int32_t n, bool with_phi, int32_t *done)
 {
-    h->last_zk_ms = 0; h->last_zk_launches = 0; h->last_launches = 0;
+    h->last_zk_ms = 0; h->last_call_ms = 0; h->last_zk_launches = 0; h->last_launches = 0;
     if (done) *done = 0;
     if (n <= 0) return 0;
     if (ensure_events(h, (size_t)n * EV_PER_SWEEP)) return 1;
@@ -326,6 +326,11 @@ int run_sweeps(ldagpu_handle h, int32_t n, bool with_phi, int32_t *done)
         h->t_counts += ms[2];
         h->t_comm += ms[3] + ms[5] + ms[7];
         h->t_phi += ms[4] + ms[6];
+    }
+    if (ran > 0) {
+        float total = 0.f;
+        CK(h, cudaEventElapsedTime(&total, h->events[0], h->events[(size_t)(ran - 1) * EV_PER_SWEEP + EV_PER_SWEEP - 1]));
+        h->last_call_ms = total;
     }
     if (done) *done = ran;
     return 0;
@@ -798,9 +803,11 @@ int ldagpu_get_timers(ldagpu_handle h, double *z_ms, double *counts_ms, double *
     return 0;
 }
 
-int ldagpu_get_last_call_stats(ldagpu_handle h, double *z_kernel_ms, int64_t *z_kernel_launches, int64_t *total_launches)
+int ldagpu_get_last_call_stats(ldagpu_handle h, double *call_ms, double *z_kernel_ms, int64_t *z_kernel_launches,
+                               int64_t *total_launches)
 {
     if (!h) return 1;
+    if (call_ms) *call_ms = h->last_call_ms;
     if (z_kernel_ms) *z_kernel_ms = h->last_zk_ms;
     if (z_kernel_launches) *z_kernel_launches = h->last_zk_launches;
     if (total_launches) *total_launches = h->last_launches;

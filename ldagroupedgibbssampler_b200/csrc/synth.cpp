@@ -64,11 +64,11 @@ template <typename F> void parallel_for(int64_t n, F f)
 
 }  // namespace
 
-extern "C" int ldagpu_synth_corpus(int64_t D, int32_t V, int32_t K_gen, double mean_len, double sigma_len,
-                                   int32_t max_len, uint64_t seed, int64_t *doc_offsets, int32_t *tokens,
-                                   int64_t capacity, int64_t *n_tokens)
+extern "C" int ldagpu_synth_corpus(int64_t D, int64_t doc_first, int32_t V, int32_t K_gen, double mean_len,
+                                   double sigma_len, int32_t max_len, uint64_t seed, int64_t *doc_offsets,
+                                   int32_t *tokens, int64_t capacity, int64_t *n_tokens)
 {
-    if (D < 0 || V < 1 || K_gen < 1 || !doc_offsets || !n_tokens || mean_len <= 0 || max_len < 1) return 1;
+    if (D < 0 || doc_first < 0 || V < 1 || K_gen < 1 || !doc_offsets || !n_tokens || mean_len <= 0 || max_len < 1) return 1;
     // topic-word distributions as cumulative tables
     std::vector<double> base((size_t)V);
     double bs = 0.0;
@@ -87,7 +87,7 @@ extern "C" int ldagpu_synth_corpus(int64_t D, int32_t V, int32_t K_gen, double m
     const double mu = std::log(mean_len) - 0.5 * sigma_len * sigma_len;
     std::vector<int32_t> len((size_t)D);
     parallel_for(D, [&](int64_t d) {
-        Rng r(mix(seed, 0x2000000 + (uint64_t)d));
+        Rng r(mix(seed, 0x2000000 + (uint64_t)(doc_first + d)));
         double l = std::exp(mu + sigma_len * r.normal());
         int64_t li = (int64_t)std::llround(l);
         len[(size_t)d] = (int32_t)std::min<int64_t>(std::max<int64_t>(li, 1), max_len);
@@ -98,7 +98,7 @@ extern "C" int ldagpu_synth_corpus(int64_t D, int32_t V, int32_t K_gen, double m
     if (!tokens) return 0;   // sizing call
     if (doc_offsets[D] > capacity) return 2;
     parallel_for(D, [&](int64_t d) {
-        Rng r(mix(seed, 0x4000000000ull + (uint64_t)d));
+        Rng r(mix(seed, 0x4000000000ull + (uint64_t)(doc_first + d)));
         std::vector<double> th((size_t)K_gen);
         double s = 0.0;
         for (int k = 0; k < K_gen; ++k) { th[(size_t)k] = r.gamma(0.1); s += th[(size_t)k]; }

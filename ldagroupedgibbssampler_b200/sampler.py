@@ -152,7 +152,8 @@ class GpuLDASampler:
         return self.startSeed
 
     def addInstances(self, training: InstanceList, *, rank: int = 0, world: int = 1,
-                     comm_id: Optional[bytes] = None, init_z: bool = True):
+                     comm_id: Optional[bytes] = None, init_z: bool = True,
+                     presharded: Optional[tuple] = None):
         """UPL:357-456: upload the corpus, draw the initial z from java.util.Random(seed) in document
         order (UPL:398-406), build the counts and draw the initial Phi (UPL:450).  With world > 1 this
         rank keeps a token-balanced contiguous shard of the documents."""
@@ -162,7 +163,12 @@ class GpuLDASampler:
         off, tokens = training.to_csr()
         self.numTypes = training.getNumTypes()
         self._global_doc_off = off
-        if world > 1:
+        self._doc_base = self._token_base = 0
+        if presharded is not None:
+            # the caller already holds only this rank's documents: (doc_base, token_base, corpus tokens)
+            self._doc_base, self._token_base, total = presharded
+            self._global_doc_off = np.array([0, total], np.int64)
+        elif world > 1:
             d0, d1 = shard_documents_by_tokens(off, world)[rank]
             off, tokens, self._doc_base, self._token_base = take_shard(off, tokens, d0, d1)
         self._doc_off, self._tokens = np.ascontiguousarray(off, np.int64), np.ascontiguousarray(tokens, np.int32)
@@ -438,9 +444,11 @@ class GpuLDASampler:
         return tuple(x.value for x in v)
 
     def getLastCallStats(self):
-        ms, zl, tl = C.c_double(0), C.c_int64(0), C.c_int64(0)
-        self._L.ldagpu_get_last_call_stats(self._h, C.byref(ms), C.byref(zl), C.byref(tl))
-        return ms.value, zl.value, tl.value
+        """(device ms of the last sample()/sampleZGivenPhi() library call, ms in the z-step kernel,
+        z-step launches, all kernel launches)"""
+        cm, ms, zl, tl = C.c_double(0), C.c_double(0), C.c_int64(0), C.c_int64(0)
+        self._L.ldagpu_get_last_call_stats(self._h, C.byref(cm), C.byref(ms), C.byref(zl), C.byref(tl))
+        return cm.value, ms.value, zl.value, tl.value
 
     # step-wise access for tests
     def _step(self, name: str):
