@@ -1,0 +1,63 @@
+"""Run under torchrun on >= 2 GPUs: the sharded library run (NCCL reduce-scatter / all-gather inside
+libldagpu) must give bit-identical z, counts, Phi and (1e-9) log-likelihood to the CPU oracle run on
+the whole corpus -- results do not depend on the number of GPUs (SURVEY 8e "Determinism").
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/multigpu_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import ldagroupedgibbssampler_b200 as L  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl")
+    ok = True
+    for scheme, osch, K, V in (("gpu_ggs", O.GGS, 100, 900), ("gpu_pcgs", O.PCGS, 400, 1300), ("gpu_ggs", O.GGS, 1000, 2100)):
+        alpha, beta, seed = 50.0 / K, 0.01, 2019
+        off, tokens = L.synth_corpus(400, V, 70.0, seed=8)
+        cfg = L.LDAConfiguration(scheme=scheme, topics=K, alpha=alpha, beta=beta, seed=seed, exec_time=0)
+        s = L.GpuLDASampler(cfg, device=local)
+        box = [L.GpuLDASampler.make_comm_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        s.addInstances(L.InstanceList.from_csr(off, tokens, V), rank=rank, world=world, comm_id=box[0])
+        s.sample(2)
+        ll = s.modelLogLikelihood()
+        n_wk, n_k, phi = s.getTypeTopicMatrix(), s.getTopicTotals(), s.getPhi().T.astype(np.float32)
+        zs = [None] * world
+        dist.all_gather_object(zs, s.get_z_flat())
+        z = np.concatenate(zs)
+        z0 = O.java_next_ints(seed, K, len(tokens))
+        nw0, _ = O.rebuild_counts(tokens, z0, V, K)
+        st = O.sweeps("contract", osch, off, tokens, z0, V, K, np.full(K, alpha), beta, seed, 1, 2,
+                      O.phi_contract(nw0, beta, seed, 0))
+        want_ll = O.log_likelihood(off, st["z"], K, V, st["n_wk"], st["n_k"], np.full(K, alpha), beta)
+        checks = dict(z=np.array_equal(z, st["z"]), n_wk=np.array_equal(n_wk, st["n_wk"]),
+                      n_k=np.array_equal(n_k, st["n_k"]), phi=np.array_equal(phi, st["phiT"]),
+                      ll=abs(ll - want_ll) <= 1e-9 * abs(want_ll))
+        if rank == 0:
+            print(scheme, K, checks, flush=True)
+        ok &= all(checks.values())
+        s.close()
+    t = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    if int(t.item()) != 1:
+        sys.exit(1)
+    if rank == 0:
+        print("multigpu_check ok, world =", world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,148 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol (no compute
+without a GPU), configuration parsing, corpus containers, sharding."""
+import ctypes as C
+import os
+import re
+import textwrap
+
+import numpy as np
+import pytest
+
+import ldagroupedgibbssampler_b200 as L
+from conftest import ROOT, make_corpus
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.load()
+    header = open(os.path.join(ROOT, "include", "ldagpu.h")).read()
+    declared = set(re.findall(r"\b(ldagpu_[a-z0-9_]+)\s*\(", header))
+    declared.discard("ldagpu_handle_s")
+    assert declared == set(L.SYMBOLS), declared ^ set(L.SYMBOLS)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert b"sm_100a" in lib.ldagpu_version()
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, never compute on the CPU."""
+    lib = L.load()
+    if lib.ldagpu_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    off, tokens = make_corpus(5, 10, 4, seed=1)
+    s = L.GpuLDASampler(L.LDAConfiguration(topics=3, alpha=0.1))
+    with pytest.raises(L.LdaGpuError, match="no CUDA device"):
+        s.addInstances(L.InstanceList.from_csr(off, tokens, 10))
+    with pytest.raises(L.LdaGpuError):
+        s.sample(1)
+
+
+def test_create_argument_validation():
+    lib = L.load()
+    h = C.c_void_p()
+    off = np.array([0, 2], np.int64)
+    tok = np.array([0, 1], np.int32)
+    al = np.array([0.1, 0.1], np.float64)
+
+    def create(K=2, V=2, beta=0.01, scheme=0, alpha=al, offs=off):
+        return lib.ldagpu_create(K, V, len(offs) - 1, L._lib.ptr(offs), L._lib.ptr(tok), L._lib.ptr(alpha), beta,
+                                 1, scheme, 0, 0, 0, C.byref(h))
+
+    assert create(K=0) != 0 and b"K" in lib.ldagpu_last_error(None)
+    assert create(scheme=7) != 0 and b"scheme" in lib.ldagpu_last_error(None)
+    assert create(beta=0.0) != 0 and b"beta" in lib.ldagpu_last_error(None)
+    assert create(alpha=np.array([0.1, -1.0])) != 0 and b"alpha" in lib.ldagpu_last_error(None)
+    assert create(offs=np.array([1, 2], np.int64)) != 0
+    assert create(K=2000, alpha=np.full(2000, 0.1)) != 0 and b"1024" in lib.ldagpu_last_error(None)
+
+
+def test_unknown_scheme_rejected():
+    with pytest.raises(ValueError):
+        L.GpuLDASampler(L.LDAConfiguration(scheme="ggs"))    # the Java schemes stay in Java
+    assert set(L.SCHEMES) == {"gpu_ggs", "gpu_pcgs"}
+    assert isinstance(L.createModel(L.LDAConfiguration(scheme="gpu_pcgs", topics=4)), L.GpuLDASampler)
+
+
+def test_cfg_parsing(tmp_path):
+    # shape of src/main/resources/configuration/plda-cats-test.cfg
+    p = tmp_path / "t.cfg"
+    p.write_text(textwrap.dedent("""
+        configs = ggs,pcgs
+        iterations = 200
+        topics = 3
+        alpha = 5
+        beta = 7
+        seed = 2019
+        exec_time = 1800 # in seconds
+        compute_likelihood = false
+        phi_mean_burnin = 10
+        save_phi_means = false
+
+        [ggs]
+        title = LDA Grouped Gibbs Sampler
+        scheme = gpu_ggs
+
+        [pcgs]
+        scheme = gpu_pcgs
+        topics = 7
+    """))
+    c = L.LDAConfiguration.from_cfg(str(p), "ggs")
+    assert (c.scheme, c.topics, c.getAlpha(), c.getBeta(), c.seed, c.iterations, c.exec_time) == \
+        ("gpu_ggs", 3, 5.0, 7.0, 2019, 200, 1800.0)
+    assert c.save_phi_mean is False          # the shipped cfgs write save_phi_means, the code reads save_phi_mean
+    c2 = L.LDAConfiguration.from_cfg(str(p), "pcgs", topics=20)     # --topics=20 (LDACommandLineParser.java:49)
+    assert (c2.scheme, c2.topics) == ("gpu_pcgs", 20)
+    assert L.LDAConfiguration.from_cfg(str(p), "pcgs").topics == 7  # sub-config wins over global
+    assert L.LDAConfiguration(topics=25).getAlpha() == 2.0          # ALPHA_DEFAULT = 50 / K
+    with pytest.raises(KeyError):
+        L.LDAConfiguration.from_cfg(str(p), "nope")
+
+
+def test_instance_list_and_loader(tmp_path):
+    p = tmp_path / "d.txt"
+    p.write_text("docno:1\tX\tWild wild CAT cat food\ndocno:2\tX\t\ndocno:3\tY\tfood 42 lion cat\n")
+    il = L.load_dataset(str(p))
+    assert il.size() == 3 and il.names == ["docno:1", "docno:2", "docno:3"] and il.labels == ["X", "X", "Y"]
+    assert [il.alphabet.lookupObject(i) for i in range(il.alphabet.size())] == ["wild", "cat", "food", "42", "lion"]
+    off, tok = il.to_csr()
+    assert off.tolist() == [0, 5, 5, 9] and tok.tolist() == [0, 0, 1, 1, 2, 2, 3, 4, 1]
+    il2 = L.load_dataset(str(p), stoplist=["cat"], keep_numbers=False)
+    assert il2.to_csr()[1].tolist() == [0, 0, 1, 1, 2]
+    back = L.InstanceList.from_csr(off, tok, 5)
+    assert back.size() == 3 and back.getNumTypes() == 5 and back.docs[2].tolist() == [2, 3, 4, 1]
+
+
+def test_cats_fixture_shape(cats):
+    off, tokens = cats
+    assert (len(off) - 1, int(tokens.max()) + 1, len(tokens)) == (23, 303, 7788)
+    assert np.diff(off).min() == 55 and np.diff(off).max() == 916
+
+
+def test_token_balanced_sharding():
+    off, tokens = make_corpus(500, 100, 40, seed=3, empty_every=17)
+    N = len(tokens)
+    for world in (1, 2, 4, 8):
+        ranges = L.shard_documents_by_tokens(off, world)
+        assert ranges[0][0] == 0 and ranges[-1][1] == 500
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        sizes = [int(off[b] - off[a]) for a, b in ranges]
+        assert sum(sizes) == N and max(sizes) - min(sizes) <= 2 * int(np.diff(off).max())
+        pieces = [L.take_shard(off, tokens, a, b) for a, b in ranges]
+        assert np.array_equal(np.concatenate([p[1] for p in pieces]), tokens)
+        for (o, t, d0, t0), (a, b) in zip(pieces, ranges):
+            assert o[0] == 0 and o[-1] == len(t) and d0 == a and t0 == off[a]
+    # degenerate: more ranks than documents
+    tiny = np.array([0, 3, 5], np.int64)
+    r = L.shard_documents_by_tokens(tiny, 4)
+    assert r[0][0] == 0 and r[-1][1] == 2 and all(a <= b for a, b in r)
+
+
+def test_synth_corpus_is_shardable_and_deterministic():
+    a_off, a_tok = L.synth_corpus(600, 300, 30.0, seed=5)
+    b_off, b_tok = L.synth_corpus(600, 300, 30.0, seed=5)
+    assert np.array_equal(a_tok, b_tok) and np.array_equal(a_off, b_off)
+    c_off, c_tok = L.synth_corpus(200, 300, 30.0, seed=5, doc_first=250)
+    assert np.array_equal(c_tok, a_tok[a_off[250]:a_off[450]])
+    assert a_tok.min() >= 0 and a_tok.max() < 300 and np.diff(a_off).min() >= 1
+    for d in range(0, 600, 97):     # bag of words: sorted inside a document
+        seg = a_tok[a_off[d]:a_off[d + 1]]
+        assert np.all(np.diff(seg) >= 0)
