@@ -1,0 +1,277 @@
+package cc.mallet.topics;
+
+// Reference-side binding of libldagpu.so (include/ldagpu.h) -- the class a maintainer of
+// clintpgeorge/LDAGroupedGibbsSampler would add for `scheme = gpu_ggs | gpu_pcgs`.
+// NOT compiled in this repository's build image (no JDK there); written against
+//   * the reference's ModifiedSimpleLDA (accessors, data, alphabet; topics/ModifiedSimpleLDA.java)
+//   * the interfaces LDAGibbsSampler (topics/LDAGibbsSampler.java:10-47) and LDASamplerWithPhi
+//     (topics/LDASamplerWithPhi.java:5-12)
+//   * the Panama Foreign Function & Memory API (JDK 22+).  On JDK 8-21 the same calls go through a
+//     ~60-line JNI stub; the C signatures are identical.
+// Factory wiring: two `case` labels in topics/tui/ParallelLDA.java:401-490, see INTEGRATION.md.
+
+import java.io.IOException;
+import java.lang.foreign.*;
+import java.lang.invoke.MethodHandle;
+
+import cc.mallet.configuration.LDAConfiguration;
+import cc.mallet.types.Alphabet;
+import cc.mallet.types.FeatureSequence;
+import cc.mallet.types.InstanceList;
+import cc.mallet.types.LabelSequence;
+
+import static java.lang.foreign.ValueLayout.*;
+
+public class GpuLDASampler extends ModifiedSimpleLDA implements LDAGibbsSampler, LDASamplerWithPhi {
+    private static final long serialVersionUID = 1L;
+
+    // ---- C ABI --------------------------------------------------------------------------------
+    private static final Linker LINKER = Linker.nativeLinker();
+    private static final SymbolLookup LIB = SymbolLookup.libraryLookup(
+            System.getProperty("ldagpu.library", "libldagpu.so"), Arena.global());
+
+    private static MethodHandle fn(String name, FunctionDescriptor d) {
+        return LINKER.downcallHandle(LIB.find(name).orElseThrow(), d);
+    }
+
+    private static final MethodHandle CREATE = fn("ldagpu_create", FunctionDescriptor.of(JAVA_INT,
+            JAVA_INT, JAVA_INT, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS, JAVA_DOUBLE, JAVA_LONG, JAVA_INT, JAVA_INT,
+            JAVA_LONG, JAVA_LONG, ADDRESS));
+    private static final MethodHandle DESTROY = fn("ldagpu_destroy", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    private static final MethodHandle LAST_ERROR = fn("ldagpu_last_error", FunctionDescriptor.of(ADDRESS, ADDRESS));
+    private static final MethodHandle INIT_Z = fn("ldagpu_init_z_java_random", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
+    private static final MethodHandle SET_Z = fn("ldagpu_set_z", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
+    private static final MethodHandle GET_Z = fn("ldagpu_get_z", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle SWEEP = fn("ldagpu_sweep", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
+    private static final MethodHandle Z_GIVEN_PHI = fn("ldagpu_sample_z_given_phi", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
+    private static final MethodHandle GET_NWK = fn("ldagpu_get_type_topic_counts", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle GET_NK = fn("ldagpu_get_topic_totals", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle GET_PHI = fn("ldagpu_get_phi", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle SET_PHI = fn("ldagpu_set_phi", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle GET_PHI_MEAN = fn("ldagpu_get_phi_mean", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle SET_MEAN_SCHEDULE = fn("ldagpu_set_phi_mean_schedule", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT));
+    private static final MethodHandle GET_THETA = fn("ldagpu_get_theta", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle LOG_LIKELIHOOD = fn("ldagpu_log_likelihood", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle LOG_POSTERIOR = fn("ldagpu_log_posterior", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle ABORT = fn("ldagpu_abort", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+
+    private final Arena arena = Arena.ofShared();
+    private MemorySegment handle = MemorySegment.NULL;
+    private final int scheme;             // 0 = gpu_ggs, 1 = gpu_pcgs
+    private long[] docOffsets;
+    private int numTokens;
+    private int noSampledPhi = 0;
+
+    public GpuLDASampler(LDAConfiguration config, boolean grouped) {
+        super(config);
+        this.scheme = grouped ? 0 : 1;
+    }
+
+    private void ck(int rc) {
+        if (rc == 0) return;
+        try {
+            MemorySegment msg = (MemorySegment) LAST_ERROR.invokeExact(handle);
+            // the reference throws IllegalStateException / IllegalArgumentException on invariant breaks
+            // (UncollapsedParallelLDA.java:475-481,1496-1497,1529-1531,1828-1830)
+            throw new IllegalStateException("libldagpu: " + msg.reinterpret(512).getString(0));
+        } catch (RuntimeException e) {
+            throw e;
+        } catch (Throwable t) {
+            throw new IllegalStateException(t);
+        }
+    }
+
+    /** UncollapsedParallelLDA.java:357-456: flatten the InstanceList to CSR and upload it. */
+    @Override
+    public void addInstances(InstanceList training) {
+        alphabet = training.getDataAlphabet();
+        numTypes = alphabet.size();
+        int D = training.size();
+        docOffsets = new long[D + 1];
+        for (int d = 0; d < D; d++)
+            docOffsets[d + 1] = docOffsets[d] + ((FeatureSequence) training.get(d).getData()).getLength();
+        numTokens = (int) docOffsets[D];
+        int[] tokens = new int[numTokens];
+        for (int d = 0; d < D; d++) {
+            FeatureSequence fs = (FeatureSequence) training.get(d).getData();
+            // the backing array may be longer than getLength() (TestInitialization.java:346-349)
+            System.arraycopy(fs.getFeatures(), 0, tokens, (int) docOffsets[d], fs.getLength());
+            data.add(new TopicAssignment(training.get(d), new LabelSequence(topicAlphabet, new int[fs.getLength()])));
+        }
+        try {
+            MemorySegment out = arena.allocate(ADDRESS);
+            ck((int) CREATE.invokeExact(numTopics, numTypes, (long) D,
+                    arena.allocateFrom(JAVA_LONG, docOffsets), arena.allocateFrom(JAVA_INT, tokens),
+                    arena.allocateFrom(JAVA_DOUBLE, alpha), beta, (long) getStartSeed(), scheme,
+                    config.getIntProperty("gpu_device", 0), 0L, 0L, out));
+            handle = out.get(ADDRESS, 0);
+            ck((int) INIT_Z.invokeExact(handle, getStartSeed()));   // Randoms(seed).nextInt(K), UPL:398-406
+        } catch (RuntimeException e) {
+            throw e;
+        } catch (Throwable t) {
+            throw new IllegalStateException(t);
+        }
+        pullZ();
+    }
+
+    /** copy z back into each document's LabelSequence: getData(), getZIndicators(), LDAUtils.getDocumentTopicCounts
+     *  (util/LDAUtils.java:1552-1571) and ModifiedSimpleLDA.java:464-477,536-547 read it from there. */
+    private void pullZ() {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment z = a.allocate(JAVA_INT, Math.max(numTokens, 1));
+            ck((int) GET_Z.invokeExact(handle, z));
+            for (int d = 0; d < data.size(); d++) {
+                int[] dst = ((LabelSequence) data.get(d).topicSequence).getFeatures();
+                MemorySegment.copy(z, JAVA_INT, docOffsets[d] * 4, dst, 0, dst.length);
+            }
+            int[] nk = new int[numTopics];
+            MemorySegment nkSeg = a.allocate(JAVA_INT, numTopics);
+            ck((int) GET_NK.invokeExact(handle, nkSeg));
+            MemorySegment.copy(nkSeg, JAVA_INT, 0, nk, 0, numTopics);
+            tokensPerTopic = nk;
+        } catch (RuntimeException e) {
+            throw e;
+        } catch (Throwable t) {
+            throw new IllegalStateException(t);
+        }
+    }
+
+    /** UncollapsedParallelLDA.java:552-943.  Diagnostics (log-posterior / log-likelihood files,
+     *  UPL:707-853) stay in Java and read the scalars from the library. */
+    @Override
+    public void sample(int iterations) throws IOException {
+        preSample();
+        int interval = config.computeLikelihood() ? Math.max(1, config.getTopicInterval(10)) : iterations;
+        if (config.savePhiMeans(false)) {
+            int burn = (int) (config.getPhiBurnInPercent(0) / 100.0 * iterations);      // UPL:206-207
+            try { ck((int) SET_MEAN_SCHEDULE.invokeExact(handle, burn, config.getPhiMeanThin(1))); }
+            catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new IllegalStateException(t); }
+        }
+        int done = 0;
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment n = a.allocate(JAVA_INT);
+            while (done < iterations && !abort) {
+                int step = Math.min(interval, iterations - done);
+                preIteration();
+                ck((int) SWEEP.invokeExact(handle, step, n));
+                done += n.get(JAVA_INT, 0);
+                currentIteration = done;
+                if (config.computeLikelihood()) loglikelihood.add(modelLogLikelihood());
+                postIteration();
+                if (n.get(JAVA_INT, 0) < step) break;
+            }
+        } catch (RuntimeException e) {
+            throw e;
+        } catch (Throwable t) {
+            throw new IllegalStateException(t);
+        }
+        pullZ();
+        postSample();
+    }
+
+    @Override
+    public void sampleZGivenPhi(int iterations) {
+        try (Arena a = Arena.ofConfined()) {
+            ck((int) Z_GIVEN_PHI.invokeExact(handle, iterations, a.allocate(JAVA_INT)));
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new IllegalStateException(t); }
+        pullZ();
+    }
+
+    @Override
+    public void setZIndicators(int[][] zIndicators) {
+        int[] flat = new int[numTokens];
+        int sum = 0;
+        for (int d = 0; d < zIndicators.length; d++) {
+            System.arraycopy(zIndicators[d], 0, flat, (int) docOffsets[d], zIndicators[d].length);
+            sum += zIndicators[d].length;
+        }
+        if (sum != numTokens)   // UPL:1828-1830
+            throw new IllegalArgumentException("Count does not sum to nr. types! Sumtotal: " + sum + " no.types: " + numTokens);
+        try (Arena a = Arena.ofConfined()) {
+            ck((int) SET_Z.invokeExact(handle, a.allocateFrom(JAVA_INT, flat), 1));
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new IllegalStateException(t); }
+        pullZ();
+    }
+
+    @Override
+    public int[][] getTypeTopicMatrix() {
+        int[][] out = new int[numTypes][numTopics];
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment m = a.allocate(JAVA_INT, (long) numTypes * numTopics);
+            ck((int) GET_NWK.invokeExact(handle, m));
+            for (int w = 0; w < numTypes; w++) MemorySegment.copy(m, JAVA_INT, (long) w * numTopics * 4, out[w], 0, numTopics);
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new IllegalStateException(t); }
+        return out;
+    }
+
+    public int[][] getTypeTopicCounts() { return getTypeTopicMatrix(); }   // UPL:226-234
+
+    @Override
+    public double[][] getPhi() {
+        double[][] out = new double[numTopics][numTypes];
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment m = a.allocate(JAVA_DOUBLE, (long) numTopics * numTypes);
+            ck((int) GET_PHI.invokeExact(handle, m));
+            for (int k = 0; k < numTopics; k++) MemorySegment.copy(m, JAVA_DOUBLE, (long) k * numTypes * 8, out[k], 0, numTypes);
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new IllegalStateException(t); }
+        return out;
+    }
+
+    @Override
+    public void setPhi(double[][] phi, Alphabet dataAlphabet, Alphabet targetAlphabet) {
+        if (!dataAlphabet.equals(getAlphabet())) throw new IllegalArgumentException("Vocabularies does not match!");   // UPL:1913-1915
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment m = a.allocate(JAVA_DOUBLE, (long) numTopics * numTypes);
+            for (int k = 0; k < numTopics; k++) MemorySegment.copy(phi[k], 0, m, JAVA_DOUBLE, (long) k * numTypes * 8, numTypes);
+            ck((int) SET_PHI.invokeExact(handle, m));
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new IllegalStateException(t); }
+    }
+
+    @Override
+    public double[][] getPhiMeans() {
+        double[][] out = new double[numTopics][numTypes];
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment m = a.allocate(JAVA_DOUBLE, (long) numTopics * numTypes);
+            MemorySegment n = a.allocate(JAVA_INT);
+            ck((int) GET_PHI_MEAN.invokeExact(handle, m, n));
+            noSampledPhi = n.get(JAVA_INT, 0);
+            if (noSampledPhi == 0) return null;                      // UPL:1955-1958
+            for (int k = 0; k < numTopics; k++) MemorySegment.copy(m, JAVA_DOUBLE, (long) k * numTypes * 8, out[k], 0, numTypes);
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new IllegalStateException(t); }
+        return out;
+    }
+
+    @Override
+    public double modelLogLikelihood() {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment v = a.allocate(JAVA_DOUBLE);
+            ck((int) LOG_LIKELIHOOD.invokeExact(handle, v));
+            return v.get(JAVA_DOUBLE, 0);
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new IllegalStateException(t); }
+    }
+
+    /** replaces the `whichModel.equals("ggs")` test of UPL:710: the GPU sampler owns its diagnostic theta */
+    public double computeLogPosterior() {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment v = a.allocate(JAVA_DOUBLE);
+            ck((int) LOG_POSTERIOR.invokeExact(handle, v));
+            return v.get(JAVA_DOUBLE, 0);
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new IllegalStateException(t); }
+    }
+
+    @Override
+    public void abort() {   // may arrive from the shutdown-hook thread (tui/ParallelLDA.java:82-101)
+        super.abort();
+        try { int rc = (int) ABORT.invokeExact(handle); } catch (Throwable t) { /* best effort */ }
+    }
+
+    @Override public void prePhi() { }
+    @Override public void postPhi() { }
+
+    public void close() {
+        try { if (!handle.equals(MemorySegment.NULL)) { int rc = (int) DESTROY.invokeExact(handle); } }
+        catch (Throwable t) { /* ignore */ }
+        handle = MemorySegment.NULL;
+        arena.close();
+    }
+}
