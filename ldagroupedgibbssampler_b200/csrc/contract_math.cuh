@@ -242,9 +242,9 @@ template <typename T> __device__ __forceinline__ T c_cos2pi(uint32_t w)
 }
 
 // One Marsaglia-Tsang attempt.  Returns true and sets g on acceptance.
-// d, c are the per-cell constants (d = aa - 1/3, c = 1/sqrt(9 d)); inv-boost shape a (< 1) if boost.
+// d, c, inva are the per-cell constants: d = aa - 1/3, c = 1/sqrt(9 d), inva = 1/a when a < 1 (boost).
 template <typename T>
-__device__ __forceinline__ bool gamma_attempt(T a, bool boost, T d, T c, uint4 w, T &g)
+__device__ __forceinline__ bool gamma_attempt(bool boost, T d, T c, T inva, uint4 w, T &g)
 {
     using M = CM<T>;
     T u1 = M::uni(w.x);
@@ -264,18 +264,42 @@ __device__ __forceinline__ bool gamma_attempt(T a, bool boost, T d, T c, uint4 w
     g = M::mul(d, v);
     if (boost) {
         T ub = M::uni(w.w);
-        g = M::mul(g, c_exp_neg<T>(M::div(c_ln<T>(ub), a)));
+        g = M::mul(g, c_exp_neg<T>(M::mul(c_ln<T>(ub), inva)));
     }
     return true;
 }
 
-template <typename T> __device__ __forceinline__ void gamma_setup(T a, bool &boost, T &d, T &c)
+// Attempt with the squeeze test only: true (and g) when `u < 1 - 0.0331 x^4` accepts the candidate,
+// false when the candidate needs the full test or was rejected -- the caller then runs c_gamma
+// for the cell from attempt 0 (same operations, same result).
+template <typename T>
+__device__ __forceinline__ bool gamma_attempt_squeeze(bool boost, T d, T c, T inva, uint4 w, T &g)
+{
+    using M = CM<T>;
+    T u1 = M::uni(w.x);
+    T x = M::mul(M::sqrt(M::mul(T(-2.0), c_ln<T>(u1))), c_cos2pi<T>(w.y));
+    T v = M::fma(c, x, T(1.0));
+    T x2 = M::mul(x, x);
+    T x4 = M::mul(x2, x2);
+    T u = M::uni(w.z);
+    if (!(v > T(0.0)) || !(u < M::fma(T(-0.0331), x4, T(1.0)))) return false;
+    v = M::mul(M::mul(v, v), v);
+    g = M::mul(d, v);
+    if (boost) {
+        T ub = M::uni(w.w);
+        g = M::mul(g, c_exp_neg<T>(M::mul(c_ln<T>(ub), inva)));
+    }
+    return true;
+}
+
+template <typename T> __device__ __forceinline__ void gamma_setup(T a, bool &boost, T &d, T &c, T &inva)
 {
     using M = CM<T>;
     boost = a < T(1.0);
     T aa = boost ? M::add(a, T(1.0)) : a;
     d = M::sub(aa, T(1.0 / 3.0));
     c = M::div(T(1.0), M::sqrt(M::mul(T(9.0), d)));
+    inva = boost ? M::div(T(1.0), a) : T(0.0);
 }
 
 // Complete draw for one cell (loops over attempts).
@@ -284,11 +308,11 @@ __device__ __forceinline__ T c_gamma(T a, uint32_t k0, uint32_t k1, unsigned lon
                                      uint32_t sweep, uint32_t stream)
 {
     bool boost;
-    T d, c, g = T(0.0);
-    gamma_setup<T>(a, boost, d, c);
+    T d, c, inva, g = T(0.0);
+    gamma_setup<T>(a, boost, d, c, inva);
     for (uint32_t attempt = 0;; ++attempt) {
         uint4 w = philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), sweep, (stream << 24) | attempt, k0, k1);
-        if (gamma_attempt<T>(a, boost, d, c, w, g)) return g;
+        if (gamma_attempt<T>(boost, d, c, inva, w, g)) return g;
     }
 }
 

@@ -44,14 +44,18 @@ phi_draw_kernel(Dims dm, const int32_t *__restrict__ n_wk, double beta, float *_
         // flattened attempt loop: a lane that rejects does not hold back lanes that accepted
         int r = 0;
         uint32_t attempt = 0;
-        bool fresh = true, boost = false;
-        double shape = 0.0, d = 0.0, c = 0.0;
+        bool fresh = true, boost = false, boost0;
+        double d = 0.0, c = 0.0, inva = 0.0, d0, c0, inva0;
+        // most cells have a zero count: their Marsaglia-Tsang constants (shape = beta) are shared
+        // (the reference precomputes the same thing, MarsagliaSparseDirichlet.java:20-29,37-38)
+        gamma_setup<double>(__dadd_rn(beta, 0.0), boost0, d0, c0, inva0);
         while (r < PHI_ROW_BLOCK) {
             const int32_t w = wb + r;
             if (w >= dm.V) break;   // padding rows stay zero
             if (fresh) {
-                shape = __dadd_rn(beta, __int2double_rn(s_n[r][threadIdx.x]));
-                gamma_setup<double>(shape, boost, d, c);
+                const int32_t n = s_n[r][threadIdx.x];
+                if (n == 0) { boost = boost0; d = d0; c = c0; inva = inva0; }
+                else gamma_setup<double>(__dadd_rn(beta, __int2double_rn(n)), boost, d, c, inva);
                 attempt = 0;
                 fresh = false;
             }
@@ -59,7 +63,7 @@ phi_draw_kernel(Dims dm, const int32_t *__restrict__ n_wk, double beta, float *_
             uint4 rnd = philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), sweep,
                                       (STREAM_PHI << 24) | attempt, seed_lo, seed_hi);
             double g;
-            if (gamma_attempt<double>(shape, boost, d, c, rnd, g)) {
+            if (gamma_attempt<double>(boost, d, c, inva, rnd, g)) {
                 float g32 = __double2float_rn(g);
                 s_g[r][threadIdx.x] = g32;
                 acc = __dadd_rn(acc, (double)g32);

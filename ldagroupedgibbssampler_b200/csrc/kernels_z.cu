@@ -64,12 +64,19 @@ __device__ __forceinline__ int draw_topic(const RowScan<NT> &rs, float U, int la
         if (rs.B[j] >= u) js = j;
     float base = 0.0f, inc = rs.incl[0];
     float q0 = rs.p[0][0], q1 = rs.p[0][1], q2 = rs.p[0][2];
-#pragma unroll
-    for (int j = 1; j < NT; ++j)
-        if (js == j) {
-            base = rs.B[j - 1]; inc = rs.incl[j];
-            q0 = rs.p[j][0]; q1 = rs.p[j][1]; q2 = rs.p[j][2];
-        }
+    // js is warp-uniform: a real branch picks the tile's registers instead of NT select chains
+#define LDAGPU_PICK(J)                                                   \
+    case J:                                                              \
+        if (J < NT) {                                                    \
+            base = rs.B[(J) > 0 ? (J) - 1 : 0]; inc = rs.incl[J < NT ? J : 0]; \
+            q0 = rs.p[J < NT ? J : 0][0]; q1 = rs.p[J < NT ? J : 0][1]; q2 = rs.p[J < NT ? J : 0][2]; \
+        }                                                                \
+        break;
+    switch (js) {
+        LDAGPU_PICK(1) LDAGPU_PICK(2) LDAGPU_PICK(3) LDAGPU_PICK(4) LDAGPU_PICK(5) LDAGPU_PICK(6) LDAGPU_PICK(7)
+        default: break;
+    }
+#undef LDAGPU_PICK
     float r = __fsub_rn(u, base);
     unsigned m = __ballot_sync(FULL, inc >= r);
     int ls = m ? __ffs(m) - 1 : 31;
@@ -300,11 +307,21 @@ cudaError_t launch_z_pcgs(const ZArgs &a, int sm_count, cudaStream_t st) { retur
 // ---------------------------------------------------------------------------------------
 // GGS theta draw: theta_d ~ Dir(n_d + alpha) from the counts before the document is resampled
 // (LDAGroupedGibbsSampler.java:60-72; ParallelDirichlet.java:46-70 = K Gammas, normalise, floor).
-// One warp per document.  Each lane walks its own 4*NT cells with a flattened attempt loop, so
-// lanes do not wait for each other's rejections; the normalising sum follows the lane/tile order
-// of the contract (lane-sequential, then xor butterfly).
+// One warp per document, lane l owning topics 4l..4l+3 of every tile (the z-step's layout).
+//   phase 1  branch-free lock step over the lane's 4*NT cells: attempt 0 of every ZERO-COUNT cell
+//            (shape = alpha_k, the vast majority; Marsaglia-Tsang constants from a per-CTA table,
+//            cf. the reference's MarsagliaSparseDirichlet.java:9-29) is settled when the squeeze
+//            accepts it (~92 %); all other cells go to a per-warp list in shared memory
+//   phase 2  the list is drained by all 32 lanes with a flattened attempt loop: a lane whose cell
+//            is accepted takes the next list entry, so rejections do not idle the warp
+//   phase 3  normalising sum in the contract's order (lane-sequential, then xor butterfly), divide,
+//            floor, coalesced float4 store
+// Cells are independent and keyed by (document, topic, attempt): the order of evaluation does not
+// change any value.  One shared-memory word per topic holds the count until the cell is drawn and
+// the Gamma value afterwards.
 // ---------------------------------------------------------------------------------------
 constexpr int TH_WARPS = 8;
+constexpr int TH_PLIST = 512;   // pending-list capacity per warp (drained early when nearly full)
 
 __global__ void __launch_bounds__(TH_WARPS * 32) theta_kernel(ThetaArgs a)
 {
@@ -312,10 +329,20 @@ __global__ void __launch_bounds__(TH_WARPS * 32) theta_kernel(ThetaArgs a)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int NT = a.dm.NT, K = a.dm.K, Ks = a.dm.Ks;
     const int ROWF = NT * TILE;
-    int *cnt = reinterpret_cast<int *>(smem_raw) + (size_t)warp * ROWF;
-    float *g = reinterpret_cast<float *>(smem_raw + (size_t)TH_WARPS * ROWF * 4) + (size_t)warp * ROWF;
-    for (int i = lane; i < ROWF; i += 32) cnt[i] = 0;
-    __syncwarp();
+    const unsigned lt_mask = (1u << lane) - 1u;
+    float *d0 = reinterpret_cast<float *>(smem_raw);
+    float *c0 = d0 + ROWF;
+    float *i0 = c0 + ROWF;
+    unsigned char *wb = smem_raw + (size_t)3 * ROWF * 4 + (size_t)warp * ((size_t)ROWF * 4 + TH_PLIST * 2);
+    int *cg = reinterpret_cast<int *>(wb);                     // count, then Gamma value bits
+    unsigned short *plist = reinterpret_cast<unsigned short *>(wb + (size_t)ROWF * 4);
+    for (int k = threadIdx.x; k < ROWF; k += blockDim.x) {
+        bool b; float dd, cc, ii;
+        gamma_setup<float>(k < K ? a.alpha[k] : 1.0f, b, dd, cc, ii);
+        d0[k] = dd; c0[k] = cc; i0[k] = ii;
+    }
+    for (int i = lane; i < ROWF; i += 32) cg[i] = 0;
+    __syncthreads();
 
     for (;;) {
         unsigned long long dd = 0;
@@ -329,45 +356,88 @@ __global__ void __launch_bounds__(TH_WARPS * 32) theta_kernel(ThetaArgs a)
             for (int i = lane; i < Ks; i += 32) trow[i] = 0.0f;
             continue;
         }
-        for (int64_t t = t0 + lane; t < t1; t += 32) atomicAdd(&cnt[a.z[t]], 1);
+        for (int64_t t = t0 + lane; t < t1; t += 32) atomicAdd(&cg[a.z[t]], 1);
         __syncwarp();
 
         const unsigned long long cell0 = (unsigned long long)(a.dm.doc_base + d) * (unsigned long long)K;
-        const int ncell = NT * 4;
-        int q = 0;
-        uint32_t attempt = 0;
-        float acc = 0.0f, shape = 0.f, dd_ = 0.f, cc_ = 0.f;
-        bool boost = false, fresh = true;
-        int k = lane * 4;
-        while (q < ncell) {
-            if (fresh) {
-                k = (q >> 2) * TILE + lane * 4 + (q & 3);
-                if (k >= K) { g[k] = 0.0f; ++q; continue; }
-                shape = __fadd_rn(__int2float_rn(cnt[k]), a.alpha[k]);
-                gamma_setup<float>(shape, boost, dd_, cc_);
-                attempt = 0;
-                fresh = false;
+        int npend = 0;
+
+        // phase 2 body: drain plist[0, npend) with a flattened attempt loop
+        auto drain = [&]() {
+            __syncwarp();
+            int next = 32, idx = lane, k = 0;
+            bool have = idx < npend, boost = false;
+            float dd_ = 0.f, cc_ = 0.f, ii_ = 0.f;
+            uint32_t attempt = 0;
+            if (have) {
+                k = plist[idx];
+                gamma_setup<float>(__fadd_rn(__int2float_rn(cg[k]), a.alpha[k]), boost, dd_, cc_, ii_);
             }
-            unsigned long long cell = cell0 + (unsigned long long)k;
-            uint4 w = philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), a.sweep,
-                                    (STREAM_THETA << 24) | attempt, a.seed_lo, a.seed_hi);
-            float gv;
-            if (gamma_attempt<float>(shape, boost, dd_, cc_, w, gv)) {
-                g[k] = gv;
-                acc = __fadd_rn(acc, gv);
-                ++q;
-                fresh = true;
-            } else {
-                ++attempt;
+            while (__any_sync(FULL, have)) {
+                bool finished = false;
+                if (have) {
+                    const unsigned long long cell = cell0 + (unsigned long long)k;
+                    uint4 w = philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), a.sweep,
+                                            (STREAM_THETA << 24) | attempt, a.seed_lo, a.seed_hi);
+                    float gv;
+                    if (gamma_attempt<float>(boost, dd_, cc_, ii_, w, gv)) {
+                        cg[k] = __float_as_int(gv);
+                        finished = true;
+                    } else {
+                        ++attempt;
+                    }
+                }
+                const unsigned fm = __ballot_sync(FULL, finished);
+                if (finished) {
+                    idx = next + __popc(fm & lt_mask);
+                    have = idx < npend;
+                    attempt = 0;
+                    if (have) {
+                        k = plist[idx];
+                        gamma_setup<float>(__fadd_rn(__int2float_rn(cg[k]), a.alpha[k]), boost, dd_, cc_, ii_);
+                    }
+                }
+                next += __popc(fm);
             }
+            npend = 0;
+            __syncwarp();
+        };
+
+        // ---- phase 1
+        for (int q = 0; q < NT * 4; ++q) {
+            const int k = (q >> 2) * TILE + lane * 4 + (q & 3);
+            const bool valid = k < K;
+            bool done = !valid;
+            if (valid && cg[k] == 0) {
+                const float ii_ = i0[k];
+                const unsigned long long cell = cell0 + (unsigned long long)k;
+                uint4 w = philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), a.sweep, STREAM_THETA << 24,
+                                        a.seed_lo, a.seed_hi);
+                float gv;
+                done = gamma_attempt_squeeze<float>(ii_ > 0.0f, d0[k], c0[k], ii_, w, gv);
+                if (done) cg[k] = __float_as_int(gv);
+            }
+            const unsigned pm = __ballot_sync(FULL, !done);
+            if (!done) plist[npend + __popc(pm & lt_mask)] = (unsigned short)k;
+            npend += __popc(pm);
+            if (npend > TH_PLIST - 32) drain();
         }
+        if (npend) drain();
         __syncwarp();
+        // ---- phase 3: sum in contract order, normalise, store
+        const float4 *g4 = reinterpret_cast<const float4 *>(cg);
+        float acc = 0.0f;
+        for (int j = 0; j < NT; ++j) {
+            const float4 v = g4[j * 32 + lane];
+            acc = __fadd_rn(acc, v.x); acc = __fadd_rn(acc, v.y);
+            acc = __fadd_rn(acc, v.z); acc = __fadd_rn(acc, v.w);
+        }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, off));
         const float sum = acc;
         for (int j = 0; j < NT; ++j) {
             int k0 = j * TILE + lane * 4;
-            float4 v = reinterpret_cast<const float4 *>(g)[j * 32 + lane];
+            float4 v = g4[j * 32 + lane];
             if (sum != 0.0f) {
                 v.x = __fdiv_rn(v.x, sum); v.y = __fdiv_rn(v.y, sum);
                 v.z = __fdiv_rn(v.z, sum); v.w = __fdiv_rn(v.w, sum);
@@ -382,7 +452,7 @@ __global__ void __launch_bounds__(TH_WARPS * 32) theta_kernel(ThetaArgs a)
             if (k0 + 2 >= K) v.z = 0.0f;
             if (k0 + 3 >= K) v.w = 0.0f;
             if (k0 < Ks) reinterpret_cast<float4 *>(trow)[k0 >> 2] = v;
-            reinterpret_cast<int4 *>(cnt)[j * 32 + lane] = make_int4(0, 0, 0, 0);
+            reinterpret_cast<int4 *>(cg)[j * 32 + lane] = make_int4(0, 0, 0, 0);
         }
         __syncwarp();
     }
@@ -391,7 +461,8 @@ __global__ void __launch_bounds__(TH_WARPS * 32) theta_kernel(ThetaArgs a)
 cudaError_t launch_theta(const ThetaArgs &a, int sm_count, cudaStream_t st)
 {
     if (a.dm.D == 0) return cudaSuccess;
-    size_t smem = (size_t)TH_WARPS * a.dm.NT * TILE * 8;
+    const size_t rowf = (size_t)a.dm.NT * TILE;
+    size_t smem = 3 * rowf * 4 + TH_WARPS * (rowf * 4 + TH_PLIST * 2);
     static size_t configured_smem = 0;
     if (smem > configured_smem) {
         cudaError_t e = cudaFuncSetAttribute(theta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
