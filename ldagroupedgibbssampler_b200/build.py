@@ -33,7 +33,12 @@ def _newer(src: str, dst: str) -> bool:
     return (not os.path.exists(dst)) or os.path.getmtime(src) > os.path.getmtime(dst)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT) -> str:
+    """defines / out: tuning variants, e.g. build(defines=["Z_STAGES=2"], out=".../libldagpu_s2.so")."""
+    global OBJ
+    if defines:
+        OBJ = os.path.join(HERE, "_obj_" + "_".join(d.replace("=", "") for d in defines))
+        force = True
     os.makedirs(OBJ, exist_ok=True)
     hdr_paths = [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
     objs = []
@@ -45,25 +50,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
         stale = force or _newer(sp, op) or any(_newer(h, op) for h in hdr_paths)
         if not stale:
             continue
-        cmd = [NVCC] + ARCH + NVFLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", sp, "-o", op]
+        cmd = ([NVCC] + ARCH + NVFLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else [])
+               + ["-c", sp, "-o", op])
         if verbose:
             print(" ".join(cmd), flush=True)
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:
-        out, _ = p.communicate()
+        text, _ = p.communicate()
         if p.returncode != 0 or verbose:
-            sys.stderr.write(f"--- {src}\n{out}\n")
+            sys.stderr.write(f"--- {src}\n{text}\n")
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    if force or procs or not os.path.exists(OUT):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-Xcompiler", "-pthread", "-ldl"]
+    if force or procs or not os.path.exists(out):
+        cmd = [NVCC] + ARCH + ["-shared", "-o", out] + objs + ["-Xcompiler", "-pthread", "-ldl"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs,
+                out=os.path.join(HERE, outs[0]) if outs else OUT))

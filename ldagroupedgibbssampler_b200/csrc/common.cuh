@@ -37,6 +37,7 @@ struct ZArgs {
     const int64_t *item_begin;// GGS: [n_items] first token of each chunk
     int64_t n_items;
     unsigned long long *work_counter;
+    int32_t *n_wk_out;        // when set (zeroed by the caller), the z-step also adds the new (w, z) counts
     uint32_t seed_lo, seed_hi, sweep;
 };
 

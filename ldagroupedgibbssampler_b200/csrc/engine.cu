@@ -206,13 +206,15 @@ int step_theta(ldagpu_handle h)
     return 0;
 }
 
-int step_z(ldagpu_handle h)
+// fused: the z kernel also accumulates n_wk (which the caller has zeroed)
+int step_z(ldagpu_handle h, bool fused = false)
 {
     CK(h, cudaMemsetAsync(h->counter.p, 0, sizeof(unsigned long long), h->stream));
     ZArgs a{};
     a.dm = h->dm; a.doc_off = h->doc_off.p; a.tokens = h->tokens.p; a.z = h->z.p; a.phiT = h->phiT.p;
     a.theta = h->theta.p; a.alpha = h->alpha_f.p; a.item_doc = h->item_doc.p; a.item_begin = h->item_begin.p;
     a.n_items = h->n_items; a.work_counter = h->counter.p;
+    a.n_wk_out = fused ? h->n_wk.p : nullptr;
     a.seed_lo = (uint32_t)h->seed; a.seed_hi = (uint32_t)(h->seed >> 32); a.sweep = (uint32_t)h->iteration;
     if (h->scheme == LDAGPU_SCHEME_GGS) {
         if (!h->theta.p) return h->fail("GGS z-step needs theta: call ldagpu_sample_theta or ldagpu_set_theta first");
@@ -227,7 +229,7 @@ int step_z(ldagpu_handle h)
 int step_counts_local(ldagpu_handle h)
 {
     CK(h, launch_counts(h->dm, h->tokens.p, h->z.p, h->n_wk.p, h->n_k.p, h->sm_count, h->stream));
-    h->last_launches += 1;
+    h->last_launches += h->dm.N > 0 ? 2 : 1;   // counts_kernel + topic_totals_kernel
     return 0;
 }
 
@@ -299,11 +301,14 @@ int run_sweeps(ldagpu_handle h, int32_t n, bool with_phi, int32_t *done)
         cudaEvent_t *ev = h->events.data() + (size_t)s * EV_PER_SWEEP;
         h->iteration += 1;
         CK(h, cudaEventRecord(ev[0], h->stream));
+        // the count rebuild is fused into the z kernel: zero n_wk first (Phi, not n_wk, feeds the z-step)
+        CK(h, cudaMemsetAsync(h->n_wk.p, 0, sizeof(int32_t) * h->n_wk.n, h->stream));
         if (h->scheme == LDAGPU_SCHEME_GGS && step_theta(h)) return 1;
         CK(h, cudaEventRecord(ev[1], h->stream));
-        if (step_z(h)) return 1;
+        if (step_z(h, true)) return 1;
         CK(h, cudaEventRecord(ev[2], h->stream));
-        if (step_counts_local(h)) return 1;
+        CK(h, launch_topic_totals(h->dm, h->n_wk.p, h->n_k.p, h->stream));
+        h->last_launches += 1;
         CK(h, cudaEventRecord(ev[3], h->stream));
         if (step_counts_exchange(h)) return 1;
         CK(h, cudaEventRecord(ev[4], h->stream));

@@ -20,23 +20,23 @@ constexpr unsigned FULL = 0xffffffffu;
 // ---------------------------------------------------------------------------------------
 constexpr int CNT_THREADS = 256;
 
-__device__ __forceinline__ void warp_aggregated_add(int32_t *n_wk, unsigned long long key, int c)
+#ifndef CNT_AGG_DEF
+#define CNT_AGG_DEF 1
+#endif
+// One atomic per distinct (w, k) cell per warp step: lanes holding the same 32-bit cell index are
+// found with match.any, their counts summed with redux, and the lowest lane issues the atomic.
+__device__ __forceinline__ void warp_aggregated_add(int32_t *n_wk, unsigned key, int c, int lane)
 {
-    // lanes with nothing to add use a key no real cell can have, distinct per lane
     unsigned m = __match_any_sync(FULL, key);
     int total = __reduce_add_sync(m, c);
-    if (total > 0 && (int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&n_wk[key], total);
+    if (total > 0 && lane == __ffs(m) - 1) atomicAdd(&n_wk[key], total);
 }
 
+template <bool AGG>
 __global__ void __launch_bounds__(CNT_THREADS)
 counts_kernel(Dims dm, const int32_t *__restrict__ tokens, const int32_t *__restrict__ z,
-              int32_t *__restrict__ n_wk, int32_t *__restrict__ n_k, int use_smem_hist)
+              int32_t *__restrict__ n_wk)
 {
-    extern __shared__ int32_t s_hist[];
-    if (use_smem_hist) {
-        for (int i = threadIdx.x; i < dm.K; i += blockDim.x) s_hist[i] = 0;
-        __syncthreads();
-    }
     const int lane = threadIdx.x & 31;
     const int64_t n4 = dm.N / 4;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -47,18 +47,14 @@ counts_kernel(Dims dm, const int32_t *__restrict__ tokens, const int32_t *__rest
         const bool ok = i < n4;
         int4 w4 = ok ? __ldg(reinterpret_cast<const int4 *>(tokens) + i) : make_int4(0, 0, 0, 0);
         int4 z4 = ok ? __ldg(reinterpret_cast<const int4 *>(z) + i) : make_int4(0, 0, 0, 0);
-        unsigned long long key[4];
+        size_t key[4];
         int c[4];
         const int ww[4] = {w4.x, w4.y, w4.z, w4.w};
         const int zz[4] = {z4.x, z4.y, z4.z, z4.w};
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-            key[s] = (unsigned long long)ww[s] * (unsigned long long)dm.Ks + (unsigned long long)zz[s];
+            key[s] = (size_t)ww[s] * (size_t)dm.Ks + (size_t)zz[s];
             c[s] = ok ? 1 : 0;
-            if (ok) {
-                if (use_smem_hist) atomicAdd(&s_hist[zz[s]], 1);
-                else atomicAdd(&n_k[zz[s]], 1);
-            }
         }
         // merge equal neighbours inside the thread (documents are bags of words: equal types adjacent)
 #pragma unroll
@@ -66,23 +62,45 @@ counts_kernel(Dims dm, const int32_t *__restrict__ tokens, const int32_t *__rest
             if (key[s] == key[s - 1]) { c[s - 1] += c[s]; c[s] = 0; }
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-            unsigned long long kk = c[s] > 0 ? key[s] : (0xffffffff00000000ull | (unsigned)lane);
-            warp_aggregated_add(n_wk, kk, c[s]);
+            if (AGG) {
+                // lanes with nothing to add use a key no cell has (cells < 2^32 - 32 is checked by the launcher)
+                warp_aggregated_add(n_wk, c[s] > 0 ? (unsigned)key[s] : 0xffffffe0u + (unsigned)lane, c[s], lane);
+            } else if (c[s] > 0) {
+                atomicAdd(&n_wk[key[s]], c[s]);
+            }
         }
     }
     // scalar tail (N % 4 tokens), done by block 0
-    if (blockIdx.x == 0) {
-        for (int64_t i = n4 * 4 + threadIdx.x; i < dm.N; i += blockDim.x) {
+    if (blockIdx.x == 0)
+        for (int64_t i = n4 * 4 + threadIdx.x; i < dm.N; i += blockDim.x)
             atomicAdd(&n_wk[(size_t)tokens[i] * dm.Ks + z[i]], 1);
-            if (use_smem_hist) atomicAdd(&s_hist[z[i]], 1);
-            else atomicAdd(&n_k[z[i]], 1);
-        }
-    }
-    if (use_smem_hist) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < dm.K; i += blockDim.x)
-            if (s_hist[i]) atomicAdd(&n_k[i], s_hist[i]);
-    }
+}
+
+// n_k = column sums of n_wk.  (A shared-memory histogram of z inside counts_kernel serialised on the
+// popular topics: 21 short-scoreboard stall cycles per issue in the round-1 profile.)
+__global__ void __launch_bounds__(128)
+topic_totals_kernel(Dims dm, const int32_t *__restrict__ n_wk, int32_t *__restrict__ n_k)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= dm.K) return;
+    int acc = 0;
+    const int rows = (dm.V + gridDim.y - 1) / gridDim.y;
+    const int w0 = blockIdx.y * rows, w1 = min(w0 + rows, dm.V);
+#pragma unroll 4
+    for (int w = w0; w < w1; ++w) acc += n_wk[(size_t)w * dm.Ks + k];
+    if (acc) atomicAdd(&n_k[k], acc);
+}
+
+cudaError_t launch_topic_totals(const Dims &dm, const int32_t *n_wk, int32_t *n_k, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(n_k, 0, sizeof(int32_t) * (size_t)dm.Ks, st);
+    if (e != cudaSuccess) return e;
+    int gy = (dm.V + 255) / 256;
+    if (gy > 1024) gy = 1024;
+    if (gy < 1) gy = 1;
+    dim3 grid((dm.K + 127) / 128, gy);
+    topic_totals_kernel<<<grid, 128, 0, st>>>(dm, n_wk, n_k);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_counts(const Dims &dm, const int32_t *tokens, const int32_t *z, int32_t *n_wk,
@@ -90,34 +108,18 @@ cudaError_t launch_counts(const Dims &dm, const int32_t *tokens, const int32_t *
 {
     cudaError_t e = cudaMemsetAsync(n_wk, 0, sizeof(int32_t) * (size_t)dm.Vp * dm.Ks, st);
     if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(n_k, 0, sizeof(int32_t) * (size_t)dm.Ks, st);
-    if (e != cudaSuccess) return e;
-    if (dm.N == 0) return cudaSuccess;
-    size_t smem = sizeof(int32_t) * (size_t)dm.K;
-    int use_smem = smem <= 48 * 1024;
-    int64_t need = (dm.N / 4 + CNT_THREADS - 1) / CNT_THREADS;
-    int64_t grid = (int64_t)sm_count * 8;
-    if (need < grid) grid = need;
-    if (grid < 1) grid = 1;
-    counts_kernel<<<(unsigned)grid, CNT_THREADS, use_smem ? smem : 0, st>>>(dm, tokens, z, n_wk, n_k, use_smem);
-    return cudaGetLastError();
-}
-
-__global__ void topic_totals_kernel(Dims dm, const int32_t *__restrict__ n_wk, int32_t *__restrict__ n_k)
-{
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= dm.K) return;
-    int acc = 0;
-    for (int w = blockIdx.y; w < dm.V; w += gridDim.y) acc += n_wk[(size_t)w * dm.Ks + k];
-    if (acc) atomicAdd(&n_k[k], acc);
-}
-cudaError_t launch_topic_totals(const Dims &dm, const int32_t *n_wk, int32_t *n_k, cudaStream_t st)
-{
-    cudaError_t e = cudaMemsetAsync(n_k, 0, sizeof(int32_t) * (size_t)dm.Ks, st);
-    if (e != cudaSuccess) return e;
-    dim3 grid((dm.K + 127) / 128, 64);
-    topic_totals_kernel<<<grid, 128, 0, st>>>(dm, n_wk, n_k);
-    return cudaGetLastError();
+    if (dm.N > 0) {
+        int64_t need = (dm.N / 4 + CNT_THREADS - 1) / CNT_THREADS;
+        int64_t grid = (int64_t)sm_count * 8;
+        if (need < grid) grid = need;
+        if (grid < 1) grid = 1;
+        const bool agg = CNT_AGG_DEF && (size_t)dm.Vp * (size_t)dm.Ks < 0xffffffe0ull;
+        if (agg) counts_kernel<true><<<(unsigned)grid, CNT_THREADS, 0, st>>>(dm, tokens, z, n_wk);
+        else counts_kernel<false><<<(unsigned)grid, CNT_THREADS, 0, st>>>(dm, tokens, z, n_wk);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return launch_topic_totals(dm, n_wk, n_k, st);
 }
 
 // getDocumentTopicMatrix: dense [D][K]

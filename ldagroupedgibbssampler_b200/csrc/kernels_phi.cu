@@ -23,61 +23,86 @@ namespace ldagpu {
 
 constexpr int PHI_THREADS = 128;
 
+// One CTA = 8 words x 128 topics.  Phase 1: every thread runs attempt 0 of its 8 cells in lock step
+// for the ZERO-COUNT cells (shape = beta: the Marsaglia-Tsang constants are shared, as the reference's
+// MarsagliaSparseDirichlet.java:20-29,37-38 precomputes them) and keeps what the squeeze accepts.
+// Phase 2: the remaining cells (non-zero counts, squeeze failures) are compacted into a CTA-wide list
+// and drained by all threads, each taking the next entry when its cell is accepted.  Cells are keyed
+// by (w, k, attempt), so the evaluation order does not change any value; the column sums are taken
+// afterwards in row order.
 __global__ void __launch_bounds__(PHI_THREADS)
 phi_draw_kernel(Dims dm, const int32_t *__restrict__ n_wk, double beta, float *__restrict__ phiT,
                 double *__restrict__ partial, int32_t row0, uint32_t seed_lo, uint32_t seed_hi, uint32_t sweep)
 {
     __shared__ int32_t s_n[PHI_ROW_BLOCK][PHI_THREADS];
     __shared__ float s_g[PHI_ROW_BLOCK][PHI_THREADS];
-    const int k = blockIdx.y * PHI_THREADS + threadIdx.x;
+    __shared__ unsigned short s_list[PHI_ROW_BLOCK * PHI_THREADS];
+    __shared__ int s_count, s_next;
+    const int tid = threadIdx.x;
+    const int k = blockIdx.y * PHI_THREADS + tid;
     const int32_t wb = row0 + blockIdx.x * PHI_ROW_BLOCK;
     const bool col_ok = k < dm.Ks;
+    if (tid == 0) { s_count = 0; s_next = PHI_THREADS; }
     // stage the 8 counts of this column with coalesced loads
 #pragma unroll
     for (int r = 0; r < PHI_ROW_BLOCK; ++r) {
         int32_t w = wb + r;
-        s_n[r][threadIdx.x] = (col_ok && w < dm.V) ? n_wk[(size_t)w * dm.Ks + k] : 0;
-        s_g[r][threadIdx.x] = 0.0f;
+        s_n[r][tid] = (col_ok && w < dm.V) ? n_wk[(size_t)w * dm.Ks + k] : 0;
+        s_g[r][tid] = 0.0f;
     }
-    double acc = 0.0;
+    __syncthreads();
+    bool boost0;
+    double d0, c0, inva0;
+    gamma_setup<double>(__dadd_rn(beta, 0.0), boost0, d0, c0, inva0);
+    // ---- phase 1
+    unsigned pend = 0;
     if (k < dm.K) {
-        // flattened attempt loop: a lane that rejects does not hold back lanes that accepted
-        int r = 0;
-        uint32_t attempt = 0;
-        bool fresh = true, boost = false, boost0;
-        double d = 0.0, c = 0.0, inva = 0.0, d0, c0, inva0;
-        // most cells have a zero count: their Marsaglia-Tsang constants (shape = beta) are shared
-        // (the reference precomputes the same thing, MarsagliaSparseDirichlet.java:20-29,37-38)
-        gamma_setup<double>(__dadd_rn(beta, 0.0), boost0, d0, c0, inva0);
-        while (r < PHI_ROW_BLOCK) {
+#pragma unroll 1
+        for (int r = 0; r < PHI_ROW_BLOCK; ++r) {
             const int32_t w = wb + r;
             if (w >= dm.V) break;   // padding rows stay zero
-            if (fresh) {
-                const int32_t n = s_n[r][threadIdx.x];
-                if (n == 0) { boost = boost0; d = d0; c = c0; inva = inva0; }
-                else gamma_setup<double>(__dadd_rn(beta, __int2double_rn(n)), boost, d, c, inva);
-                attempt = 0;
-                fresh = false;
+            bool done = false;
+            if (s_n[r][tid] == 0) {
+                const unsigned long long cell = (unsigned long long)w * (unsigned long long)dm.K + (unsigned long long)k;
+                uint4 rnd = philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), sweep, STREAM_PHI << 24, seed_lo, seed_hi);
+                double g;
+                done = gamma_attempt_squeeze<double>(boost0, d0, c0, inva0, rnd, g);
+                if (done) s_g[r][tid] = __double2float_rn(g);
             }
-            const unsigned long long cell = (unsigned long long)w * (unsigned long long)dm.K + (unsigned long long)k;
-            uint4 rnd = philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), sweep,
-                                      (STREAM_PHI << 24) | attempt, seed_lo, seed_hi);
-            double g;
-            if (gamma_attempt<double>(boost, d, c, inva, rnd, g)) {
-                float g32 = __double2float_rn(g);
-                s_g[r][threadIdx.x] = g32;
-                acc = __dadd_rn(acc, (double)g32);
-                ++r;
-                fresh = true;
-            } else {
-                ++attempt;
-            }
+            pend |= (done ? 0u : 1u) << r;
         }
     }
+    // ---- phase 2
+    {
+        int pos = pend ? atomicAdd(&s_count, __popc(pend)) : 0;
+        while (pend) {
+            const int r = __ffs(pend) - 1;
+            pend &= pend - 1;
+            s_list[pos++] = (unsigned short)(r * PHI_THREADS + tid);
+        }
+    }
+    __syncthreads();
+    const int total = s_count;
+    int idx = tid;
+    while (idx < total) {
+        const int e = s_list[idx];
+        const int r = e / PHI_THREADS, col = e % PHI_THREADS;
+        const unsigned long long cell = (unsigned long long)(wb + r) * (unsigned long long)dm.K +
+                                        (unsigned long long)(blockIdx.y * PHI_THREADS + col);
+        const double g = c_gamma<double>(__dadd_rn(beta, __int2double_rn(s_n[r][col])), seed_lo, seed_hi, cell,
+                                         sweep, STREAM_PHI);
+        s_g[r][col] = __double2float_rn(g);
+        idx = atomicAdd(&s_next, 1);
+    }
+    __syncthreads();
     if (col_ok) {
+        double acc = 0.0;
 #pragma unroll
-        for (int r = 0; r < PHI_ROW_BLOCK; ++r)
-            phiT[(size_t)(wb + r) * dm.Ks + k] = s_g[r][threadIdx.x];
+        for (int r = 0; r < PHI_ROW_BLOCK; ++r) {
+            const float g32 = s_g[r][tid];
+            acc = __dadd_rn(acc, (double)g32);
+            phiT[(size_t)(wb + r) * dm.Ks + k] = g32;
+        }
         partial[(size_t)(wb / PHI_ROW_BLOCK) * dm.Ks + k] = acc;
     }
 }

@@ -20,74 +20,117 @@
 namespace ldagpu {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int Z_WARPS = 8;    // warps per CTA
-constexpr int Z_STAGES = 3;   // Phi^T rows in flight per warp
+// Tuning (measured on B200, PubMed-shaped K=1000 / Enron-shaped K=400, profiles/r01_tuning.md): the
+// kernel is bound by shuffle/shared-pipe latency, not by row fetches (83 % of them hit L2), so
+// resident warps matter more than prefetch depth: 1 ring slot and 4 CTAs/SM (32 warps, 64
+// registers, 72 B of spills at K=1000) beat 3 slots and 2 CTAs/SM by 20 %.
+#ifndef Z_STAGES_DEF
+#define Z_STAGES_DEF 1
+#endif
+#ifndef Z_MINB_DEF
+#define Z_MINB_DEF 4
+#endif
+constexpr int Z_WARPS = 8;               // warps per CTA
+constexpr int Z_STAGES = Z_STAGES_DEF;   // Phi^T row slots per warp (the row also lives in registers)
 
 template <int NT> struct RowScan {
-    float p[NT][4];   // lane-local inclusive prefix of the 4 owned scores, per tile
-    float incl[NT];   // inclusive warp scan of the lane totals, per tile
-    float B[NT];      // inclusive cumulative tile totals (warp-uniform)
+    float p[NT][4];   // lane-local inclusive prefix of the 4 owned scores, per tile (p[j][3] = lane total)
+    float B;          // cumulative tile total through tile (lane >> 2) & 7
+    float S;          // total over all tiles
 };
 
+// Scores, lane-local prefixes, and the cumulative tile totals (contract: DESIGN.md 4.2).
+// Tile totals come from a distributed butterfly: after the xor-16/8/4 exchanges lane l works for
+// tile (l>>2)&7 only, so 8 tiles cost 4+2+1+1+1 shuffles instead of 8 x 5.
 template <int NT>
 __device__ __forceinline__ void scan_scores(const float4 (&a)[NT], const float4 (&ph)[NT],
                                             RowScan<NT> &rs, int lane)
 {
-    float base = 0.0f;
+    float t[8];
 #pragma unroll
-    for (int j = 0; j < NT; ++j) {
-        float p0 = __fmul_rn(a[j].x, ph[j].x);
-        float p1 = __fadd_rn(p0, __fmul_rn(a[j].y, ph[j].y));
-        float p2 = __fadd_rn(p1, __fmul_rn(a[j].z, ph[j].z));
-        float p3 = __fadd_rn(p2, __fmul_rn(a[j].w, ph[j].w));
-        rs.p[j][0] = p0; rs.p[j][1] = p1; rs.p[j][2] = p2; rs.p[j][3] = p3;
-        float x = p3;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            float y = __shfl_up_sync(FULL, x, off);
-            if (lane >= off) x = __fadd_rn(x, y);
+    for (int j = 0; j < 8; ++j) {
+        if (j < NT) {
+            float p0 = __fmul_rn(a[j < NT ? j : 0].x, ph[j < NT ? j : 0].x);
+            float p1 = __fadd_rn(p0, __fmul_rn(a[j < NT ? j : 0].y, ph[j < NT ? j : 0].y));
+            float p2 = __fadd_rn(p1, __fmul_rn(a[j < NT ? j : 0].z, ph[j < NT ? j : 0].z));
+            float p3 = __fadd_rn(p2, __fmul_rn(a[j < NT ? j : 0].w, ph[j < NT ? j : 0].w));
+            rs.p[j < NT ? j : 0][0] = p0; rs.p[j < NT ? j : 0][1] = p1;
+            rs.p[j < NT ? j : 0][2] = p2; rs.p[j < NT ? j : 0][3] = p3;
+            t[j] = p3;
+        } else {
+            t[j] = 0.0f;
         }
-        rs.incl[j] = x;
-        base = __fadd_rn(base, __shfl_sync(FULL, x, 31));
-        rs.B[j] = base;
     }
+    const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
+    float u[4], v[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float keep = h16 ? t[4 + i] : t[i], send = h16 ? t[i] : t[4 + i];
+        u[i] = __fadd_rn(keep, __shfl_xor_sync(FULL, send, 16));
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        float keep = h8 ? u[2 + i] : u[i], send = h8 ? u[i] : u[2 + i];
+        v[i] = __fadd_rn(keep, __shfl_xor_sync(FULL, send, 8));
+    }
+    float w;
+    {
+        float keep = h4 ? v[1] : v[0], send = h4 ? v[0] : v[1];
+        w = __fadd_rn(keep, __shfl_xor_sync(FULL, send, 4));
+    }
+    w = __fadd_rn(w, __shfl_xor_sync(FULL, w, 2));
+    w = __fadd_rn(w, __shfl_xor_sync(FULL, w, 1));
+    // inclusive scan over the tile index: quads hold tiles, so the offsets are 4, 8, 16 lanes
+#pragma unroll
+    for (int off = 4; off < 32; off <<= 1) {
+        float y = __shfl_up_sync(FULL, w, off);
+        if (lane >= off) w = __fadd_rn(w, y);
+    }
+    rs.B = w;
+    rs.S = __shfl_sync(FULL, w, 31);
 }
 
 // first k with cumsum_k >= U * sum, searched tile -> lane -> element
 template <int NT>
 __device__ __forceinline__ int draw_topic(const RowScan<NT> &rs, float U, int lane, int K)
 {
-    float u = __fmul_rn(U, rs.B[NT - 1]);
-    int js = NT - 1;
-#pragma unroll
-    for (int j = NT - 2; j >= 0; --j)
-        if (rs.B[j] >= u) js = j;
-    float base = 0.0f, inc = rs.incl[0];
-    float q0 = rs.p[0][0], q1 = rs.p[0][1], q2 = rs.p[0][2];
-    // js is warp-uniform: a real branch picks the tile's registers instead of NT select chains
-#define LDAGPU_PICK(J)                                                   \
-    case J:                                                              \
-        if (J < NT) {                                                    \
-            base = rs.B[(J) > 0 ? (J) - 1 : 0]; inc = rs.incl[J < NT ? J : 0]; \
-            q0 = rs.p[J < NT ? J : 0][0]; q1 = rs.p[J < NT ? J : 0][1]; q2 = rs.p[J < NT ? J : 0][2]; \
-        }                                                                \
+    const float u = __fmul_rn(U, rs.S);
+    const unsigned mt = __ballot_sync(FULL, rs.B >= u);
+    int js = (mt ? __ffs(mt) - 1 : 31) >> 2;
+    if (js > NT - 1) js = NT - 1;
+    float base = __shfl_sync(FULL, rs.B, js > 0 ? 4 * js - 1 : 0);
+    if (js == 0) base = 0.0f;
+    const float r = __fsub_rn(u, base);
+    // js is warp-uniform: a real branch picks the tile's registers
+    float q0 = rs.p[0][0], q1 = rs.p[0][1], q2 = rs.p[0][2], inc = rs.p[0][3];
+#define LDAGPU_PICK(J)                                                                         \
+    case J:                                                                                    \
+        if (J < NT) {                                                                          \
+            q0 = rs.p[J < NT ? J : 0][0]; q1 = rs.p[J < NT ? J : 0][1];                         \
+            q2 = rs.p[J < NT ? J : 0][2]; inc = rs.p[J < NT ? J : 0][3];                        \
+        }                                                                                      \
         break;
     switch (js) {
         LDAGPU_PICK(1) LDAGPU_PICK(2) LDAGPU_PICK(3) LDAGPU_PICK(4) LDAGPU_PICK(5) LDAGPU_PICK(6) LDAGPU_PICK(7)
         default: break;
     }
 #undef LDAGPU_PICK
-    float r = __fsub_rn(u, base);
-    unsigned m = __ballot_sync(FULL, inc >= r);
-    int ls = m ? __ffs(m) - 1 : 31;
+    // inclusive scan of the chosen tile's lane totals
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        float y = __shfl_up_sync(FULL, inc, off);
+        if (lane >= off) inc = __fadd_rn(inc, y);
+    }
+    const unsigned m = __ballot_sync(FULL, inc >= r);
+    const int ls = m ? __ffs(m) - 1 : 31;
     float prev = __shfl_up_sync(FULL, inc, 1);
     if (lane == 0) prev = 0.0f;
-    float r2 = __fsub_rn(r, prev);
+    const float r2 = __fsub_rn(r, prev);
     int i = 3;
     if (q2 >= r2) i = 2;
     if (q1 >= r2) i = 1;
     if (q0 >= r2) i = 0;
-    int k = __shfl_sync(FULL, TILE * js + 4 * lane + i, ls);
+    const int k = __shfl_sync(FULL, TILE * js + 4 * lane + i, ls);
     return k < K ? k : K - 1;
 }
 
@@ -103,7 +146,7 @@ template <int NT, bool PCGS> __host__ __device__ constexpr size_t z_cta_smem()
 }
 
 template <int NT, bool PCGS>
-__global__ void __launch_bounds__(Z_WARPS * 32) z_kernel(ZArgs a)
+__global__ void __launch_bounds__(Z_WARPS * 32, (PCGS && NT == 8) ? 2 : Z_MINB_DEF) z_kernel(ZArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -257,7 +300,13 @@ __global__ void __launch_bounds__(Z_WARPS * 32) z_kernel(ZArgs a)
                     }
                 }
             }
-            if (valid) a.z[t] = znew;
+            if (valid) {
+                a.z[t] = znew;
+                // fused count rebuild (the reference adds its +-1 deltas inside the token loop too,
+                // UncollapsedParallelLDA.java:1505,1542): fire-and-forget reductions ride on the
+                // memory system this issue-bound kernel leaves idle
+                if (a.n_wk_out) atomicAdd(&a.n_wk_out[(size_t)w * Ks + znew], 1);
+            }
         }
         if (PCGS) {
             // leave the histogram clean for the next document
@@ -403,7 +452,8 @@ __global__ void __launch_bounds__(TH_WARPS * 32) theta_kernel(ThetaArgs a)
             __syncwarp();
         };
 
-        // ---- phase 1
+        // ---- phase 1 (pending cells are remembered in a per-lane bit mask: NT <= 8 => 32 cells)
+        unsigned pend = 0;
         for (int q = 0; q < NT * 4; ++q) {
             const int k = (q >> 2) * TILE + lane * 4 + (q & 3);
             const bool valid = k < K;
@@ -417,12 +467,31 @@ __global__ void __launch_bounds__(TH_WARPS * 32) theta_kernel(ThetaArgs a)
                 done = gamma_attempt_squeeze<float>(ii_ > 0.0f, d0[k], c0[k], ii_, w, gv);
                 if (done) cg[k] = __float_as_int(gv);
             }
-            const unsigned pm = __ballot_sync(FULL, !done);
-            if (!done) plist[npend + __popc(pm & lt_mask)] = (unsigned short)k;
-            npend += __popc(pm);
-            if (npend > TH_PLIST - 32) drain();
+            pend |= (done ? 0u : 1u) << q;
         }
-        if (npend) drain();
+        // ---- phase 2: compact the pending cells of all lanes into the list, TH_PLIST at a time
+        {
+            int mine = __popc(pend), incl = mine;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                int y = __shfl_up_sync(FULL, incl, off);
+                if (lane >= off) incl += y;
+            }
+            const int total = __shfl_sync(FULL, incl, 31);
+            for (int lo = 0; lo < total; lo += TH_PLIST) {
+                int pos = incl - mine;
+                unsigned bits = pend;
+                while (bits) {
+                    const int q = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    if (pos >= lo && pos < lo + TH_PLIST)
+                        plist[pos - lo] = (unsigned short)((q >> 2) * TILE + lane * 4 + (q & 3));
+                    ++pos;
+                }
+                npend = min(total - lo, TH_PLIST);
+                drain();
+            }
+        }
         __syncwarp();
         // ---- phase 3: sum in contract order, normalise, store
         const float4 *g4 = reinterpret_cast<const float4 *>(cg);

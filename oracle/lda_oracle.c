@@ -279,21 +279,26 @@ void oracle_doc_topic_counts(int64_t D, const int64_t *doc_off, const int32_t *z
  * Contract categorical draw.  Restates the reference's
  *   sum = sum_k score_k; sample = U*sum; walk k until sample - cumsum_k <= 0
  * (topics/LDAGroupedGibbsSampler.java:96-113, topics/UncollapsedParallelLDA.java:1507-1526)
- * as "first k with cumsum_k >= U*sum" over a fixed three-level fp32 prefix tree:
- *   tile = 128 topics, lane l of 32 owns 4 consecutive topics of the tile;
- *   lane-local sequential prefix p0..p3; Kogge-Stone inclusive scan of the 32 lane totals;
- *   tile bases accumulated sequentially.
+ * as "first k with cumsum_k >= U*sum" over a fixed fp32 prefix tree:
+ *   tile = 128 topics, lane l of 32 owns 4 consecutive topics of the tile; lane-local sequential
+ *     prefix p0..p3, lane total t = p3;
+ *   tile totals, 8 tiles at a time, by a distributed butterfly over the 32 lanes: xor 16 (lanes
+ *     with bit 4 clear keep tiles 0-3, the others tiles 4-7), xor 8 (2 tiles kept), xor 4 (1 tile
+ *     kept: lane l now works for tile (l>>2)&7), xor 2, xor 1;
+ *   cumulative tile totals: Kogge-Stone over the tile index (lane offsets 4, 8, 16), plus the
+ *     carry of the previous groups of 8 tiles;
+ *   inside the chosen tile: Kogge-Stone inclusive scan of its 32 lane totals.
+ * Search tile -> lane -> element; clamp to K-1.
  * ------------------------------------------------------------------------------------------ */
 static int32_t draw_topic_contract(const float *a, const float *phirow, int32_t K, float U,
-                                   float *scratch /* NT*(128+32+1) floats */)
+                                   float *scratch /* NT*128 + ceil(NT/8)*33 floats */)
 {
     int NT = (K + 127) / 128;
-    float *p = scratch;               /* [NT][32][4] */
-    float *incl = scratch + NT * 128; /* [NT][32] */
-    float *B = incl + NT * 32;        /* [NT] inclusive tile cumsum */
-    float base = 0.0f;
-    for (int j = 0; j < NT; ++j) {
-        float x[32], y[32];
+    int NG = (NT + 7) / 8;
+    float *p = scratch;                 /* [NT][32][4] lane-local prefixes */
+    float *Bf = scratch + NT * 128;     /* [NG][32] cumulative tile totals as the lanes hold them */
+    float *carry = Bf + NG * 32;        /* [NG] cumulative total before each group */
+    for (int j = 0; j < NT; ++j)
         for (int l = 0; l < 32; ++l) {
             float run = 0.0f;
             for (int i = 0; i < 4; ++i) {
@@ -302,26 +307,65 @@ static int32_t draw_topic_contract(const float *a, const float *phirow, int32_t 
                 run = (i == 0) ? s : run + s;
                 p[(j * 32 + l) * 4 + i] = run;
             }
-            x[l] = run;
         }
-        for (int off = 1; off < 32; off <<= 1) {
+    float cr = 0.0f;
+    for (int g = 0; g < NG; ++g) {
+        float t[8][32], uA[32][4], vB[32][2], wC[32], wD[32], T[32], x[32], y[32];
+        for (int tau = 0; tau < 8; ++tau)
+            for (int l = 0; l < 32; ++l) {
+                int j = 8 * g + tau;
+                t[tau][l] = j < NT ? p[(j * 32 + l) * 4 + 3] : 0.0f;
+            }
+        for (int l = 0; l < 32; ++l) {
+            int hi = (l >> 4) & 1;
+            for (int i = 0; i < 4; ++i) uA[l][i] = t[4 * hi + i][l] + t[4 * hi + i][l ^ 16];
+        }
+        for (int l = 0; l < 32; ++l) {
+            int h = (l >> 3) & 1;
+            for (int i = 0; i < 2; ++i) vB[l][i] = uA[l][2 * h + i] + uA[l ^ 8][2 * h + i];
+        }
+        for (int l = 0; l < 32; ++l) { int h = (l >> 2) & 1; wC[l] = vB[l][h] + vB[l ^ 4][h]; }
+        for (int l = 0; l < 32; ++l) wD[l] = wC[l] + wC[l ^ 2];
+        for (int l = 0; l < 32; ++l) T[l] = wD[l] + wD[l ^ 1];
+        memcpy(x, T, sizeof x);
+        for (int off = 4; off < 32; off <<= 1) {
             for (int l = 0; l < 32; ++l) y[l] = (l >= off) ? x[l] + x[l - off] : x[l];
             memcpy(x, y, sizeof x);
         }
-        memcpy(incl + j * 32, x, sizeof x);
-        base = base + x[31];
-        B[j] = base;
+        carry[g] = cr;
+        for (int l = 0; l < 32; ++l) Bf[g * 32 + l] = (g == 0) ? x[l] : cr + x[l];
+        cr = Bf[g * 32 + 31];
     }
-    float S = base;
+    float S = cr;
     float u = U * S;
     int js = NT - 1;
-    for (int j = 0; j < NT; ++j)
-        if (B[j] >= u) { js = j; break; }
-    float r = u - (js > 0 ? B[js - 1] : 0.0f);
+    float base = 0.0f;
+    int found = 0;
+    for (int g = 0; g < NG && !found; ++g)
+        for (int l = 0; l < 32; ++l)
+            if (Bf[g * 32 + l] >= u) {
+                int tau = l >> 2;
+                js = 8 * g + tau;
+                base = tau > 0 ? Bf[g * 32 + 4 * tau - 1] : carry[g];
+                found = 1;
+                break;
+            }
+    if (!found || js > NT - 1) { /* unreachable for finite inputs (u <= S); kept total */
+        js = NT - 1;
+        int g = js / 8, tau = js % 8;
+        base = tau > 0 ? Bf[g * 32 + 4 * tau - 1] : carry[g];
+    }
+    float r = u - base;
+    float x[32], y[32];
+    for (int l = 0; l < 32; ++l) x[l] = p[(js * 32 + l) * 4 + 3];
+    for (int off = 1; off < 32; off <<= 1) {
+        for (int l = 0; l < 32; ++l) y[l] = (l >= off) ? x[l] + x[l - off] : x[l];
+        memcpy(x, y, sizeof x);
+    }
     int ls = 31;
     for (int l = 0; l < 32; ++l)
-        if (incl[js * 32 + l] >= r) { ls = l; break; }
-    float r2 = r - (ls > 0 ? incl[js * 32 + ls - 1] : 0.0f);
+        if (x[l] >= r) { ls = l; break; }
+    float r2 = r - (ls > 0 ? x[ls - 1] : 0.0f);
     int is = 3;
     for (int i = 0; i < 4; ++i)
         if (p[(js * 32 + ls) * 4 + i] >= r2) { is = i; break; }
