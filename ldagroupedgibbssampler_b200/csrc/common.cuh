@@ -55,6 +55,12 @@ struct ThetaArgs {
 cudaError_t launch_theta(const ThetaArgs &a, int sm_count, cudaStream_t st);
 cudaError_t launch_z_ggs(const ZArgs &a, int sm_count, cudaStream_t st);
 cudaError_t launch_z_pcgs(const ZArgs &a, int sm_count, cudaStream_t st);
+// K > 1024 (kernels_z_big.cu): row and per-document vector in shared memory
+cudaError_t launch_theta_big(const ThetaArgs &a, int sm_count, cudaStream_t st);
+cudaError_t launch_z_ggs_big(const ZArgs &a, int sm_count, cudaStream_t st);
+cudaError_t launch_z_pcgs_big(const ZArgs &a, int sm_count, cudaStream_t st);
+// largest K the dense z-step can hold in shared memory (row + vector [+ counts] per warp)
+inline int max_dense_topics(bool pcgs) { return pcgs ? 18000 : 27000; }
 cudaError_t launch_counts(const Dims &dm, const int32_t *tokens, const int32_t *z, int32_t *n_wk,
                           int32_t *n_k, int sm_count, cudaStream_t st);
 cudaError_t launch_topic_totals(const Dims &dm, const int32_t *n_wk, int32_t *n_k, cudaStream_t st);

@@ -400,7 +400,7 @@ double lgamma_stirling_host(double z)
 // =============================================================================================
 extern "C" {
 
-const char *ldagpu_version(void) { return "libldagpu 0.1 (sm_100a; GGS + PCGS dense z-step, K <= 1024)"; }
+const char *ldagpu_version(void) { return "libldagpu 0.2 (sm_100a; GGS + PCGS dense z-step)"; }
 
 const char *ldagpu_last_error(ldagpu_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -420,7 +420,8 @@ int ldagpu_create(int32_t K, int32_t V, int64_t D, const int64_t *doc_offsets, c
     if (!out || !doc_offsets || (!tokens && D > 0 && doc_offsets[D] > 0) || !alpha) return bail("null argument");
     if (K < 1 || V < 1 || D < 0) return bail("K, V must be >= 1 and D >= 0");
     if (scheme != LDAGPU_SCHEME_GGS && scheme != LDAGPU_SCHEME_PCGS) return bail("unknown scheme");
-    if ((K + TILE - 1) / TILE > MAX_REG_TILES) return bail("K > 1024 is not supported by the dense z-step yet");
+    if (K > max_dense_topics(scheme == LDAGPU_SCHEME_PCGS))
+        return bail("K is too large for the dense z-step (one Phi row + one document vector per warp in shared memory)");
     if (!(beta > 0.0)) return bail("beta must be > 0");   // ParallelRandoms.java:61-63
     for (int k = 0; k < K; ++k)
         if (!(alpha[k] > 0.0)) return bail("alpha must be > 0");

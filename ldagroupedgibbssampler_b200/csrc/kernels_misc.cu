@@ -230,14 +230,16 @@ cudaError_t launch_ll_doc(const Dims &dm, const int64_t *doc_off, const int32_t 
                           int sm_count, cudaStream_t st)
 {
     (void)sm_count;
-    size_t smem = sizeof(int32_t) * (size_t)dm.Ks * (RED_THREADS / 32);
+    int warps = RED_THREADS / 32;
+    while (warps > 1 && sizeof(int32_t) * (size_t)dm.Ks * warps > 200 * 1024) warps /= 2;
+    size_t smem = sizeof(int32_t) * (size_t)dm.Ks * warps;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(ll_doc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    ll_doc_kernel<<<n_partials, RED_THREADS, smem, st>>>(dm, doc_off, z, alpha, alpha_sum, partials);
+    ll_doc_kernel<<<n_partials, warps * 32, smem, st>>>(dm, doc_off, z, alpha, alpha_sum, partials);
     return cudaGetLastError();
 }
 
@@ -331,14 +333,16 @@ cudaError_t launch_lp_theta(const Dims &dm, const int64_t *doc_off, const int32_
                             int n_partials, int sm_count, cudaStream_t st)
 {
     (void)sm_count;
-    size_t smem = sizeof(int32_t) * (size_t)dm.Ks * (RED_THREADS / 32);
+    int warps = RED_THREADS / 32;
+    while (warps > 1 && sizeof(int32_t) * (size_t)dm.Ks * warps > 200 * 1024) warps /= 2;
+    size_t smem = sizeof(int32_t) * (size_t)dm.Ks * warps;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(lp_theta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    lp_theta_kernel<<<n_partials, RED_THREADS, smem, st>>>(dm, doc_off, z, theta, alpha, partials);
+    lp_theta_kernel<<<n_partials, warps * 32, smem, st>>>(dm, doc_off, z, theta, alpha, partials);
     return cudaGetLastError();
 }
 

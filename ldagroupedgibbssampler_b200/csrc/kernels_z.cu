@@ -347,7 +347,7 @@ template <bool PCGS> static cudaError_t launch_z_any(const ZArgs &a, int sm_coun
     if (nt <= 2) return launch_z_t<2, PCGS>(a, sm_count, st);
     if (nt <= 4) return launch_z_t<4, PCGS>(a, sm_count, st);
     if (nt <= 8) return launch_z_t<8, PCGS>(a, sm_count, st);
-    return cudaErrorInvalidValue;   // K > 1024: dense register path not built
+    return PCGS ? launch_z_pcgs_big(a, sm_count, st) : launch_z_ggs_big(a, sm_count, st);
 }
 
 cudaError_t launch_z_ggs(const ZArgs &a, int sm_count, cudaStream_t st) { return launch_z_any<false>(a, sm_count, st); }
@@ -530,6 +530,7 @@ __global__ void __launch_bounds__(TH_WARPS * 32) theta_kernel(ThetaArgs a)
 cudaError_t launch_theta(const ThetaArgs &a, int sm_count, cudaStream_t st)
 {
     if (a.dm.D == 0) return cudaSuccess;
+    if (a.dm.NT > MAX_REG_TILES) return launch_theta_big(a, sm_count, st);
     const size_t rowf = (size_t)a.dm.NT * TILE;
     size_t smem = 3 * rowf * 4 + TH_WARPS * (rowf * 4 + TH_PLIST * 2);
     static size_t configured_smem = 0;

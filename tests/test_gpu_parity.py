@@ -155,6 +155,27 @@ def test_whole_sweeps_bit_exact_synthetic(oracle, scheme, osch, K):
     s.close()
 
 
+@pytest.mark.parametrize("scheme,osch,K", [("gpu_ggs", 0, 1025), ("gpu_pcgs", 1, 1500), ("gpu_ggs", 0, 2600),
+                                           ("gpu_pcgs", 1, 2049)])
+def test_large_k_dense_path_bit_exact(oracle, scheme, osch, K):
+    """K > 1024: Phi^T row staged in shared memory, tile totals in groups of 8 tiles with a carry."""
+    off, tokens = make_corpus(40, 300, 30, seed=K, empty_every=9)
+    V, alpha, beta, seed = 300, 50.0 / K, 0.01, 5
+    s = _sampler(scheme, off, tokens, V, K, alpha, beta, seed)
+    z0 = s.get_z_flat()
+    phi0 = s.getPhi().T.astype(np.float32).copy()
+    s.sample(2)
+    st = oracle.sweeps("contract", osch, off, tokens, z0, V, K, np.full(K, alpha), beta, seed, 1, 2, phi0)
+    assert np.array_equal(s.get_z_flat(), st["z"])
+    assert np.array_equal(s.getTypeTopicMatrix(), st["n_wk"])
+    assert np.array_equal(s.getPhi().T.astype(np.float32), st["phiT"])
+    if osch == 0:
+        assert np.array_equal(s.getTheta().astype(np.float32), st["theta"])
+    want_ll = oracle.log_likelihood(off, st["z"], K, V, st["n_wk"], st["n_k"], np.full(K, alpha), beta)
+    assert abs(s.modelLogLikelihood() - want_ll) <= 1e-9 * abs(want_ll)
+    s.close()
+
+
 def test_set_z_round_trip_and_invariants(oracle):
     """TestInitialization.java:458-555: setZIndicators reproduces counts and LL; ParanoidTest invariants."""
     off, tokens = make_corpus(80, 250, 35, seed=3)

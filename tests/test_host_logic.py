@@ -52,7 +52,7 @@ def test_create_argument_validation():
     assert create(beta=0.0) != 0 and b"beta" in lib.ldagpu_last_error(None)
     assert create(alpha=np.array([0.1, -1.0])) != 0 and b"alpha" in lib.ldagpu_last_error(None)
     assert create(offs=np.array([1, 2], np.int64)) != 0
-    assert create(K=2000, alpha=np.full(2000, 0.1)) != 0 and b"1024" in lib.ldagpu_last_error(None)
+    assert create(K=30000, alpha=np.full(30000, 0.1)) != 0 and b"too large" in lib.ldagpu_last_error(None)
 
 
 def test_unknown_scheme_rejected():
