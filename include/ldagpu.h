@@ -30,6 +30,10 @@ typedef struct ldagpu_handle_s *ldagpu_handle;
 
 #define LDAGPU_SCHEME_GGS 0  /* GGS:47-132, GGS:139-209 */
 #define LDAGPU_SCHEME_PCGS 1 /* UPL:1466-1545, PCGS:48-118 */
+/* PCGS with the reference's sparse z-step (topics/SpaliasUncollapsedParallelLDA.java:39-60,124-312:
+ * per-type alias table over alpha_k*phi_kw + sparse cumulative sum over the topics with n_dk > 0)
+ * and the PCGS Phi draw: the path for K in the thousands. */
+#define LDAGPU_SCHEME_SPALIAS 2
 
 /* version / build info ("libldagpu x.y sm_100a") */
 const char *ldagpu_version(void);

@@ -124,6 +124,11 @@ struct ldagpu_handle_s {
     DevBuf<int64_t> doc_off, item_begin;
     DevBuf<int32_t> tokens, z, n_wk, n_k, item_doc, scratch_i32;
     DevBuf<float> phiT, theta, alpha_f;
+    // sparse scheme: per-type alias tables over alpha_k * phi_kw and the build scratch
+    DevBuf<float> alias_ps, type_norm;
+    DevBuf<int32_t> alias_al, alias_stack;
+    DevBuf<double> alias_bs;
+    int max_doc_len = 0;
     DevBuf<double> alpha_d, partial, seg, topic_sum, phi_mean, red, red_out, scratch_f64;
     DevBuf<unsigned long long> counter;
     DevBuf<int> bad;
@@ -219,10 +224,22 @@ int step_z(ldagpu_handle h, bool fused = false)
     if (h->scheme == LDAGPU_SCHEME_GGS) {
         if (!h->theta.p) return h->fail("GGS z-step needs theta: call ldagpu_sample_theta or ldagpu_set_theta first");
         CK(h, launch_z_ggs(a, h->sm_count, h->stream));
+    } else if (h->scheme == LDAGPU_SCHEME_SPALIAS) {
+        CK(h, launch_z_spalias(a, h->alias_ps.p, h->alias_al.p, h->type_norm.p, h->max_doc_len, h->sm_count, h->stream));
     } else {
         CK(h, launch_z_pcgs(a, h->sm_count, h->stream));
     }
     if (h->n_items) { h->last_launches += 1; h->last_zk_launches += 1; }
+    return 0;
+}
+
+// sparse scheme: the alias tables follow every change of Phi (SpaliasUncollapsedParallelLDA.java:39-60)
+int step_alias(ldagpu_handle h)
+{
+    if (h->scheme != LDAGPU_SCHEME_SPALIAS) return 0;
+    CK(h, launch_alias_build(h->dm, h->alpha_f.p, h->phiT.p, h->alias_ps.p, h->alias_al.p, h->type_norm.p,
+                             h->alias_bs.p, h->alias_stack.p, h->sm_count, h->stream));
+    h->last_launches += 1;
     return 0;
 }
 
@@ -271,6 +288,7 @@ int step_phi(ldagpu_handle h, bool accumulate_mean, cudaEvent_t *ev)
         const size_t slice = (size_t)(h->dm.Vp / h->world) * h->dm.Ks;
         NK(h, g_nccl.AllGather(h->phiT.p + (size_t)h->rank * slice, h->phiT.p, slice, ncclFloat, h->comm, h->stream));
     }
+    if (step_alias(h)) return 1;
     if (ev) CK(h, cudaEventRecord(ev[3], h->stream));
     return 0;
 }
@@ -419,9 +437,11 @@ int ldagpu_create(int32_t K, int32_t V, int64_t D, const int64_t *doc_offsets, c
     auto bail = [&](const std::string &m) { g_create_error = m; return 1; };
     if (!out || !doc_offsets || (!tokens && D > 0 && doc_offsets[D] > 0) || !alpha) return bail("null argument");
     if (K < 1 || V < 1 || D < 0) return bail("K, V must be >= 1 and D >= 0");
-    if (scheme != LDAGPU_SCHEME_GGS && scheme != LDAGPU_SCHEME_PCGS) return bail("unknown scheme");
-    if (K > max_dense_topics(scheme == LDAGPU_SCHEME_PCGS))
+    if (scheme != LDAGPU_SCHEME_GGS && scheme != LDAGPU_SCHEME_PCGS && scheme != LDAGPU_SCHEME_SPALIAS)
+        return bail("unknown scheme");
+    if (scheme != LDAGPU_SCHEME_SPALIAS && K > max_dense_topics(scheme == LDAGPU_SCHEME_PCGS))
         return bail("K is too large for the dense z-step (one Phi row + one document vector per warp in shared memory)");
+    if (scheme == LDAGPU_SCHEME_SPALIAS && K > (1 << 20)) return bail("K is too large");
     if (!(beta > 0.0)) return bail("beta must be > 0");   // ParallelRandoms.java:61-63
     for (int k = 0; k < K; ++k)
         if (!(alpha[k] > 0.0)) return bail("alpha must be > 0");
@@ -471,6 +491,19 @@ int ldagpu_create(int32_t K, int32_t V, int64_t D, const int64_t *doc_offsets, c
         CK(h, h->red_out.alloc(8));
         CK(h, h->counter.alloc(1));
         CK(h, h->bad.alloc(1));
+        for (int64_t d = 0; d < D; ++d)
+            h->max_doc_len = (int)std::max<int64_t>(h->max_doc_len, doc_offsets[d + 1] - doc_offsets[d]);
+        if (scheme == LDAGPU_SCHEME_SPALIAS) {
+            const size_t T = (size_t)alias_scratch_threads(dm, h->sm_count);
+            CK(h, h->alias_ps.alloc((size_t)dm.Vp * dm.Ks));
+            CK(h, h->alias_al.alloc((size_t)dm.Vp * dm.Ks));
+            CK(h, h->type_norm.alloc((size_t)dm.Vp));
+            CK(h, h->alias_bs.alloc(T * (size_t)K));
+            CK(h, h->alias_stack.alloc(T * (size_t)K));
+            CK(h, cudaMemset(h->alias_ps.p, 0, sizeof(float) * h->alias_ps.n));
+            CK(h, cudaMemset(h->alias_al.p, 0, sizeof(int32_t) * h->alias_al.n));
+            CK(h, cudaMemset(h->type_norm.p, 0, sizeof(float) * h->type_norm.n));
+        }
         CK(h, cudaMemcpy(h->doc_off.p, doc_offsets, sizeof(int64_t) * ((size_t)D + 1), cudaMemcpyHostToDevice));
         CK(h, cudaMemset(h->tokens.p, 0, sizeof(int32_t) * h->tokens.n));
         CK(h, cudaMemset(h->z.p, 0, sizeof(int32_t) * h->z.n));
@@ -512,6 +545,7 @@ int ldagpu_destroy(ldagpu_handle h)
     h->alpha_f.release(); h->alpha_d.release(); h->partial.release(); h->seg.release(); h->topic_sum.release();
     h->phi_mean.release(); h->red.release(); h->red_out.release(); h->scratch_f64.release();
     h->counter.release(); h->bad.release();
+    h->alias_ps.release(); h->type_norm.release(); h->alias_al.release(); h->alias_stack.release(); h->alias_bs.release();
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -692,6 +726,7 @@ int ldagpu_set_phi(ldagpu_handle h, const double *phi)
     CK(h, h->scratch_f64.alloc(cells));
     CK(h, cudaMemcpyAsync(h->scratch_f64.p, phi, sizeof(double) * cells, cudaMemcpyHostToDevice, h->stream));
     CK(h, launch_import_phi(h->dm, h->scratch_f64.p, h->phiT.p, h->stream));
+    if (step_alias(h)) return 1;
     int rc = sync_check(h);
     h->scratch_f64.release();
     // UPL:1897-1903: setPhi resets the running mean

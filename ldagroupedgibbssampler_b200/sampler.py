@@ -22,7 +22,8 @@ from . import _lib
 from ._lib import LdaGpuError, ptr
 from .corpus import InstanceList
 
-SCHEMES = {"gpu_ggs": 0, "gpu_pcgs": 1}
+# gpu_spalias = PCGS with the reference's sparse z-step (scheme "spalias", topics/tui/ParallelLDA.java:401-490)
+SCHEMES = {"gpu_ggs": 0, "gpu_pcgs": 1, "gpu_spalias": 2}
 
 
 @dataclass

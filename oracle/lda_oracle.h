@@ -130,6 +130,17 @@ void oracle_baseline_sweeps(int scheme, int64_t D, int32_t V, int32_t K, const i
                             double *phi_seconds);
 int oracle_max_threads(void);
 
+/* ---- sparse PCGS z-step ("spalias"), lda_oracle_sparse.c -------------------------------------
+ * reference: topics/SpaliasUncollapsedParallelLDA.java:39-60,124-312, util/OptimizedGentleAliasMethod.java:52-107 */
+void oracle_alias_build_contract(int32_t V, int32_t K, const double *alpha, const float *phiT, float *ps,
+                                 int32_t *al, float *type_norm);
+void oracle_z_spalias_contract(int64_t D, const int64_t *doc_off, const int32_t *tokens, int32_t *z,
+                               int32_t K, const float *phiT, const float *ps, const int32_t *al,
+                               const float *type_norm, uint64_t seed, uint32_t sweep, int64_t token_base);
+void oracle_z_spalias_faithful(int64_t D, int32_t V, const int64_t *doc_off, const int32_t *tokens, int32_t *z,
+                               int32_t K, const double *alpha, const double *phiT, uint64_t seed,
+                               uint32_t sweep, int64_t token_base);
+
 #ifdef __cplusplus
 }
 #endif

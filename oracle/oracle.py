@@ -16,13 +16,14 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "liblda_oracle.so")
 
-GGS, PCGS = 0, 1
+GGS, PCGS, SPALIAS = 0, 1, 2
 STREAM_Z, STREAM_THETA, STREAM_PHI = 1, 2, 3
 
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the Makefile beside this file (gcc only)."""
-    srcs = [os.path.join(_HERE, f) for f in ("lda_oracle.c", "lda_oracle.h", "contract_math.inc")]
+    srcs = [os.path.join(_HERE, f) for f in ("lda_oracle.c", "lda_oracle_sparse.c", "lda_oracle.h",
+                                             "contract_math.inc")]
     stale = (not os.path.exists(_SO)) or any(
         os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
     if force or stale:
@@ -88,6 +89,9 @@ def lib():
     sig("oracle_baseline_sweeps", None, C.c_int, i64, i32, i32, _i64p, _i32p, _i32p, _f64p, f64,
         u64, i32, i32, C.POINTER(f64), C.POINTER(f64))
     sig("oracle_max_threads", C.c_int)
+    sig("oracle_alias_build_contract", None, i32, i32, _f64p, _f32p, _f32p, _i32p, _f32p)
+    sig("oracle_z_spalias_contract", None, i64, _i64p, _i32p, _i32p, i32, _f32p, _f32p, _i32p, _f32p, u64, u32, i64)
+    sig("oracle_z_spalias_faithful", None, i64, i32, _i64p, _i32p, _i32p, i32, _f64p, _f64p, u64, u32, i64)
     _lib = L
     return L
 
@@ -185,6 +189,34 @@ def z_pcgs_faithful(doc_off, tokens, z, K, alpha, phiT, seed, sweep, token_base=
     return z
 
 
+def alias_build_contract(phiT, alpha):
+    """Per-type alias tables over alpha_k * phi_kw: returns (ps float32[V][K], al int32[V][K], type_norm float32[V])."""
+    V, K = phiT.shape
+    ps, al, tn = np.zeros((V, K), np.float32), np.zeros((V, K), np.int32), np.zeros(V, np.float32)
+    lib().oracle_alias_build_contract(V, K, np.ascontiguousarray(alpha, np.float64),
+                                      np.ascontiguousarray(phiT, np.float32), ps, al, tn)
+    return ps, al, tn
+
+
+def z_spalias_contract(doc_off, tokens, z, K, alpha, phiT, seed, sweep, token_base=0, tables=None):
+    z = np.array(z, np.int32, copy=True)
+    phiT = np.ascontiguousarray(phiT, np.float32)
+    ps, al, tn = tables if tables is not None else alias_build_contract(phiT, alpha)
+    lib().oracle_z_spalias_contract(len(doc_off) - 1, np.ascontiguousarray(doc_off, np.int64),
+                                    np.ascontiguousarray(tokens, np.int32), z, K, phiT, ps, al, tn, seed, sweep,
+                                    token_base)
+    return z
+
+
+def z_spalias_faithful(doc_off, tokens, z, K, alpha, phiT, seed, sweep, token_base=0):
+    z = np.array(z, np.int32, copy=True)
+    phiT = np.ascontiguousarray(phiT, np.float64)
+    lib().oracle_z_spalias_faithful(len(doc_off) - 1, phiT.shape[0], np.ascontiguousarray(doc_off, np.int64),
+                                    np.ascontiguousarray(tokens, np.int32), z, K,
+                                    np.ascontiguousarray(alpha, np.float64), phiT, seed, sweep, token_base)
+    return z
+
+
 def phi_contract(n_wk, beta, seed, sweep):
     V, K = n_wk.shape
     out = np.zeros((V, K), np.float32)
@@ -223,6 +255,17 @@ def sweeps(mode, scheme, doc_off, tokens, z, V, K, alpha, beta, seed, first_swee
     theta = np.zeros((D, K), ft)
     n_wk = np.zeros((V, K), np.int32)
     n_k = np.zeros(K, np.int32)
+    if scheme == SPALIAS:
+        # same sweep as PCGS with the sparse z-step (the alias tables are rebuilt from every new Phi)
+        for s in range(n_sweeps):
+            it = first_sweep + s
+            if mode == "contract":
+                z = z_spalias_contract(doc_off, tokens, z, K, alpha, phiT, seed, it)
+            else:
+                z = z_spalias_faithful(doc_off, tokens, z, K, alpha, phiT, seed, it)
+            n_wk, n_k = rebuild_counts(tokens, z, V, K)
+            phiT = phi_contract(n_wk, beta, seed, it) if mode == "contract" else phi_faithful(n_wk, beta, seed, it)
+        return dict(z=z, phiT=phiT, theta=theta, n_wk=n_wk, n_k=n_k)
     fn = lib().oracle_sweeps_contract if mode == "contract" else lib().oracle_sweeps_faithful
     fn(scheme, D, V, K, np.ascontiguousarray(doc_off, np.int64),
        np.ascontiguousarray(tokens, np.int32), z, np.ascontiguousarray(alpha, np.float64), beta,

@@ -176,6 +176,30 @@ def test_large_k_dense_path_bit_exact(oracle, scheme, osch, K):
     s.close()
 
 
+@pytest.mark.parametrize("K,V,D,mean_len", [(20, 303, 23, 300), (300, 800, 120, 60), (1500, 400, 60, 40), (4000, 300, 50, 150)])
+def test_sparse_pcgs_bit_exact(oracle, K, V, D, mean_len):
+    """gpu_spalias: alias tables and sparse z-step bit-exact against the oracle, whole sweeps included."""
+    off, tokens = make_corpus(D, V, mean_len, seed=K + 2, empty_every=11)
+    alpha, beta, seed = 50.0 / K, 0.01, 17
+    s = _sampler("gpu_spalias", off, tokens, V, K, alpha, beta, seed)
+    z0 = s.get_z_flat()
+    phi0 = s.getPhi().T.astype(np.float32).copy()
+    s._step("next_iteration")
+    s._step("sample_z")
+    want = oracle.z_spalias_contract(off, tokens, z0, K, np.full(K, alpha), phi0, seed, 1)
+    assert np.array_equal(s.get_z_flat(), want)
+    s.set_z_flat(z0, redraw_phi=False)
+    s._L.ldagpu_set_iteration(s._h, 0)
+    s.sample(3)
+    st = oracle.sweeps("contract", oracle.SPALIAS, off, tokens, z0, V, K, np.full(K, alpha), beta, seed, 1, 3, phi0)
+    assert np.array_equal(s.get_z_flat(), st["z"])
+    assert np.array_equal(s.getTypeTopicMatrix(), st["n_wk"]) and np.array_equal(s.getTopicTotals(), st["n_k"])
+    assert np.array_equal(s.getPhi().T.astype(np.float32), st["phiT"])
+    want_ll = oracle.log_likelihood(off, st["z"], K, V, st["n_wk"], st["n_k"], np.full(K, alpha), beta)
+    assert abs(s.modelLogLikelihood() - want_ll) <= 1e-9 * abs(want_ll)
+    s.close()
+
+
 def test_set_z_round_trip_and_invariants(oracle):
     """TestInitialization.java:458-555: setZIndicators reproduces counts and LL; ParanoidTest invariants."""
     off, tokens = make_corpus(80, 250, 35, seed=3)

@@ -212,3 +212,86 @@ def test_contract_and_faithful_chains_agree_statistically(oracle, cats, scheme):
     c, f = np.array(res["contract"]), np.array(res["faithful"])
     spread = max(c.std(), f.std(), 1.0)
     assert abs(c.mean() - f.mean()) < 4 * spread / np.sqrt(len(c)) + 5e-4 * abs(f.mean())
+
+
+# ---- sparse PCGS z-step ("spalias") ---------------------------------------------------------------
+def test_alias_tables_reproduce_the_prior(oracle):
+    """WalkerAliasTableTest / OptimizedGentleAliasMethod.main: the table must encode alpha_k*phi_kw / norm."""
+    rng = np.random.default_rng(1)
+    V, K = 40, 37
+    phi = rng.dirichlet(np.full(V, 0.05), size=K).T.astype(np.float32).copy()      # [V][K]
+    alpha = rng.random(K) + 0.01
+    ps, al, tn = oracle.alias_build_contract(phi, alpha)
+    for w in range(V):
+        p = np.zeros(K)
+        for i in range(K):
+            if al[w, i] == i:
+                p[i] += 1.0 / K
+            else:
+                p[i] += ps[w, i] / K
+                p[al[w, i]] += (1.0 - ps[w, i]) / K
+        want = alpha.astype(np.float32).astype(np.float64) * phi[w]
+        assert abs(tn[w] - want.sum()) <= 1e-6 * want.sum()
+        assert np.allclose(p, want / want.sum(), atol=2e-6)
+        assert ps[w].min() >= 0 and ps[w].max() <= 1.0 + 1e-6 and al[w].min() >= 0 and al[w].max() < K
+
+
+def test_spalias_contract_vs_faithful_and_invariants(oracle):
+    off, tokens = make_corpus(80, 150, 30, seed=11, empty_every=9)
+    V, K, beta = 150, 64, 0.05
+    alpha = np.full(K, 0.2)
+    z = oracle.java_next_ints(5, K, len(tokens))
+    n_wk, _ = oracle.rebuild_counts(tokens, z, V, K)
+    phi = oracle.phi_contract(n_wk, beta, 5, 0)
+    a = oracle.z_spalias_contract(off, tokens, z, K, alpha, phi, 5, 1)
+    b = oracle.z_spalias_faithful(off, tokens, z, K, alpha.astype(np.float32).astype(np.float64),
+                                  phi.astype(np.float64), 5, 1)
+    assert a.min() >= 0 and a.max() < K and (a == b).mean() > 0.99
+    assert np.array_equal(a, oracle.z_spalias_contract(off, tokens, z, K, alpha, phi, 5, 1))
+    st = oracle.sweeps("contract", oracle.SPALIAS, off, tokens, z, V, K, alpha, beta, 5, 1, 3, phi)
+    assert st["n_wk"].sum() == len(tokens) and np.array_equal(st["n_wk"].sum(axis=0), st["n_k"])
+
+
+def test_spalias_targets_the_same_conditional_as_dense_pcgs(oracle):
+    """One token resampled many times: the sparse mixture (alias prior + sparse likelihood) and the dense
+    walk must give the same distribution over topics (chi-square on a single-document corpus)."""
+    K, V = 12, 5
+    rng = np.random.default_rng(3)
+    phi = rng.dirichlet(np.full(V, 0.5), size=K).T.astype(np.float32).copy()
+    alpha = np.full(K, 0.3)
+    base = np.array([0, 0, 3, 3, 3, 7], np.int32)            # the other tokens of the document
+    n = 4000
+    off = np.arange(n + 1, dtype=np.int64) * (len(base) + 1)
+    tokens = np.tile(np.concatenate([[2], np.zeros(len(base), np.int32)]), n).astype(np.int32)
+    z0 = np.tile(np.concatenate([[5], base]), n).astype(np.int32)
+    zs = oracle.z_spalias_contract(off, tokens, z0, K, alpha, phi, 9, 1)[:: len(base) + 1]
+    zd = oracle.z_pcgs_contract(off, tokens, z0, K, alpha, phi, 9, 1)[:: len(base) + 1]
+    cnt = np.bincount(base, minlength=K)
+    p = (cnt + alpha) * phi[2]
+    p /= p.sum()
+    for draw in (zs, zd):
+        obs = np.bincount(draw, minlength=K)
+        keep = p * n > 5
+        chi2 = ((obs[keep] - p[keep] * n) ** 2 / (p[keep] * n)).sum()
+        assert chi2 < stats.chi2.ppf(1 - 1e-5, keep.sum() - 1)
+
+
+def test_spalias_and_dense_chains_agree_statistically(oracle, cats):
+    off, tokens = cats
+    K, V, beta = 8, 303, 0.5
+    al = np.full(K, 0.5)
+    res = {oracle.PCGS: [], oracle.SPALIAS: []}
+    for seed in range(5):
+        z0 = oracle.java_next_ints(seed + 1, K, len(tokens))
+        n_wk0, _ = oracle.rebuild_counts(tokens, z0, V, K)
+        phi0 = oracle.phi_contract(n_wk0, beta, seed, 0)
+        for sch in res:
+            st = oracle.sweeps("contract", sch, off, tokens, z0, V, K, al, beta, seed, 1, 50, phi0)
+            lls = []
+            for it in range(51, 66):
+                st = oracle.sweeps("contract", sch, off, tokens, st["z"], V, K, al, beta, seed, it, 1, st["phiT"])
+                lls.append(oracle.log_likelihood(off, st["z"], K, V, st["n_wk"], st["n_k"], al, beta))
+            res[sch].append(np.mean(lls))
+    a, b = np.array(res[oracle.PCGS]), np.array(res[oracle.SPALIAS])
+    spread = max(a.std(), b.std(), 1.0)
+    assert abs(a.mean() - b.mean()) < 4 * spread / np.sqrt(len(a)) + 5e-4 * abs(a.mean())
