@@ -39,6 +39,9 @@ WORKLOADS = {
                  D=1500, V=12419, mean_len=1267.0, K=100, scheme="gpu_ggs", alpha=1.0, beta=0.01),
     "enron": dict(desc="Enron-shaped PCGS K=400 (BASELINE.json configs[2])",
                   D=39861, V=28102, mean_len=161.0, K=400, scheme="gpu_pcgs", alpha=0.125, beta=0.01),
+    "wiki8": dict(desc="Wikipedia-shaped sparse PCGS K=10000, V=100000, per-GPU shard = 1/8 of the ~4M-doc corpus "
+                       "(BASELINE.json configs[4] at 8 GPUs)",
+                  D=500000, V=100000, mean_len=250.0, K=10000, scheme="gpu_spalias", alpha=0.005, beta=0.01),
 }
 METRIC = "token-topic samples/sec per Gibbs sweep"
 UNIT = "tokens/s"
@@ -119,6 +122,29 @@ def cpu_baseline(wl, off, tokens, budget_tokens, n_shard_tokens):
     o, t = off[: d1 + 1].copy(), tokens[: off[d1]].copy()
     K, V = wl["K"], wl["V"]
     z = O.java_next_ints(SEED, K, len(t))
+    if wl["scheme"] == "gpu_spalias":
+        # the reference's own sparse sampler (SpaliasUncollapsedParallelLDA), restated in double: per sweep
+        # alias tables for all V types + Phi draw (both O(K*V)); per token the sparse walk
+        alpha = np.full(K, wl["alpha"])
+        n_wk, _ = O.rebuild_counts(t, z, V, K)
+        t0 = time.perf_counter()
+        phi = O.phi_faithful(n_wk, wl["beta"], SEED, 0)
+        ps = time.perf_counter() - t0
+        del n_wk
+        t0 = time.perf_counter()
+        O.z_spalias_faithful(o[:1], t[:0], z[:0], K, alpha, phi, SEED, 1)      # alias build only
+        ab = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        O.z_spalias_faithful(o, t, z, K, alpha, phi, SEED, 1)
+        zs = max(time.perf_counter() - t0 - ab, 1e-9)
+        nt = O.lib().oracle_max_threads()
+        per_tok = zs / max(len(t), 1)
+        value = n_shard_tokens / (n_shard_tokens * per_tok + ps + ab)
+        return {"value": value, "unit": UNIT, "cores": nt, "kind": "port",
+                "sample": f"{d1} documents / {len(t)} tokens of the same corpus, 1 sweep of the sparse sampler: "
+                          f"token loop {zs:.3f}s ({per_tok * 1e9:.1f} ns/token), alias tables {ab:.3f}s and Phi draw "
+                          f"{ps:.3f}s (both full K*V); rate extrapolated to the {n_shard_tokens}-token shard; C "
+                          f"restatement (oracle/lda_oracle_sparse.c), not the Java reference"}
     sch = O.GGS if wl["scheme"] == "gpu_ggs" else O.PCGS
     zs, ps, nt = O.baseline_sweeps(sch, o, t, z, V, K, np.full(K, wl["alpha"]), wl["beta"], SEED, 1)
     per_tok = zs / max(len(t), 1)
@@ -273,11 +299,20 @@ def main():
     # ---- roofline of the dominant kernel (z-step) -------------------------------------------
     peak, peak_src = peaks()
     bytes_per_token = 4 * wl["K"] + 12                      # one fp32 K-vector + w + z in + z out
+    mean_nnz = None
+    if wl["scheme"] == "gpu_spalias":
+        # SURVEY 8(d) sparse z-step: 12 + 8*nnz_d + 16 bytes per token, nnz_d measured on a sample of documents
+        zf, dsamp = s.get_z_flat(), min(len(off) - 1, 20000)
+        nnz = np.array([len(np.unique(zf[off[d]:off[d + 1]])) for d in range(dsamp)], np.float64)
+        lens = np.diff(off[: dsamp + 1]).astype(np.float64)
+        mean_nnz = float((nnz * lens).sum() / max(lens.sum(), 1.0))
+        bytes_per_token = 28 + 8 * mean_nnz
     alg_bytes = bytes_per_token * max(sizes)                # one launch processes the rank's shard
     achieved = alg_bytes / (zk_ms_per_launch / 1e3) / 1e9
     traffic = traffic_from_profiles(args.workload)
-    roofline = {"bound": "hbm", "kernel": "z_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src,
+    roofline = {"bound": "hbm", "kernel": "z_spalias_kernel" if mean_nnz is not None else "z_kernel",
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src, "mean_nnz_d": mean_nnz,
                 "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_token": bytes_per_token,
                 "kernel_ms_per_launch": zk_ms_per_launch, "kernel_share_of_step": zk_ms / max(call_ms, 1e-9),
                 "traffic": traffic,

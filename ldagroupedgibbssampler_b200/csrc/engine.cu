@@ -126,7 +126,8 @@ struct ldagpu_handle_s {
     DevBuf<float> phiT, theta, alpha_f;
     // sparse scheme: per-type alias tables over alpha_k * phi_kw and the build scratch
     DevBuf<float> alias_ps, type_norm;
-    DevBuf<int32_t> alias_al, alias_stack;
+    DevBuf<int32_t> alias_al, alias_stack, active_types, sparse_lists;
+    int32_t n_active_types = 0;
     DevBuf<double> alias_bs;
     int max_doc_len = 0;
     DevBuf<double> alpha_d, partial, seg, topic_sum, phi_mean, red, red_out, scratch_f64;
@@ -225,7 +226,8 @@ int step_z(ldagpu_handle h, bool fused = false)
         if (!h->theta.p) return h->fail("GGS z-step needs theta: call ldagpu_sample_theta or ldagpu_set_theta first");
         CK(h, launch_z_ggs(a, h->sm_count, h->stream));
     } else if (h->scheme == LDAGPU_SCHEME_SPALIAS) {
-        CK(h, launch_z_spalias(a, h->alias_ps.p, h->alias_al.p, h->type_norm.p, h->max_doc_len, h->sm_count, h->stream));
+        CK(h, launch_z_spalias(a, h->alias_ps.p, h->alias_al.p, h->type_norm.p, h->sparse_lists.p, h->max_doc_len,
+                               h->sm_count, h->stream));
     } else {
         CK(h, launch_z_pcgs(a, h->sm_count, h->stream));
     }
@@ -238,7 +240,8 @@ int step_alias(ldagpu_handle h)
 {
     if (h->scheme != LDAGPU_SCHEME_SPALIAS) return 0;
     CK(h, launch_alias_build(h->dm, h->alpha_f.p, h->phiT.p, h->alias_ps.p, h->alias_al.p, h->type_norm.p,
-                             h->alias_bs.p, h->alias_stack.p, h->sm_count, h->stream));
+                             h->alias_bs.p, h->alias_stack.p, h->active_types.p, h->n_active_types, h->sm_count,
+                             h->stream));
     h->last_launches += 1;
     return 0;
 }
@@ -347,7 +350,9 @@ int run_sweeps(ldagpu_handle h, int32_t n, bool with_phi, int32_t *done)
         h->t_z += ms[0] + ms[1];
         h->last_zk_ms += ms[1];
         h->t_counts += ms[2];
-        h->t_comm += ms[3] + ms[5] + ms[7];
+        // ms[7] = Phi all-gather + (sparse scheme) alias-table build: on one GPU it is all table build
+        h->t_comm += ms[3] + ms[5] + (h->world > 1 ? ms[7] : 0.0f);
+        if (h->world == 1) h->t_phi += ms[7];
         h->t_phi += ms[4] + ms[6];
     }
     if (ran > 0) {
@@ -500,6 +505,18 @@ int ldagpu_create(int32_t K, int32_t V, int64_t D, const int64_t *doc_offsets, c
             CK(h, h->type_norm.alloc((size_t)dm.Vp));
             CK(h, h->alias_bs.alloc(T * (size_t)K));
             CK(h, h->alias_stack.alloc(T * (size_t)K));
+            CK(h, h->sparse_lists.alloc(spalias_list_bytes(dm, h->max_doc_len, h->sm_count) / sizeof(int32_t)));
+            // only the types that occur in this rank's tokens are ever looked up
+            std::vector<char> seen((size_t)V, 0);
+            for (int64_t i = 0; i < dm.N; ++i)
+                if (tokens[i] >= 0 && tokens[i] < V) seen[(size_t)tokens[i]] = 1;
+            std::vector<int32_t> act;
+            for (int32_t w = 0; w < V; ++w)
+                if (seen[(size_t)w]) act.push_back(w);
+            h->n_active_types = (int32_t)act.size();
+            CK(h, h->active_types.alloc(std::max<size_t>(act.size(), 1)));
+            if (!act.empty())
+                CK(h, cudaMemcpy(h->active_types.p, act.data(), sizeof(int32_t) * act.size(), cudaMemcpyHostToDevice));
             CK(h, cudaMemset(h->alias_ps.p, 0, sizeof(float) * h->alias_ps.n));
             CK(h, cudaMemset(h->alias_al.p, 0, sizeof(int32_t) * h->alias_al.n));
             CK(h, cudaMemset(h->type_norm.p, 0, sizeof(float) * h->type_norm.n));
@@ -546,6 +563,7 @@ int ldagpu_destroy(ldagpu_handle h)
     h->phi_mean.release(); h->red.release(); h->red_out.release(); h->scratch_f64.release();
     h->counter.release(); h->bad.release();
     h->alias_ps.release(); h->type_norm.release(); h->alias_al.release(); h->alias_stack.release(); h->alias_bs.release();
+    h->active_types.release(); h->sparse_lists.release();
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;

@@ -18,67 +18,124 @@ namespace ldagpu {
 constexpr unsigned FULL = 0xffffffffu;
 
 // ---------------------------------------------------------------------------------------
-// Alias tables.  One thread per word type runs the reference's sequential stack algorithm
-// (it is order dependent, so it stays sequential per type; types are independent).  Scratch per
-// thread: b[K] fp64 and one int stack[K] holding the "low" stack from the front and the "high"
-// stack from the back; scratch is interleaved across threads (element i of thread t at i*T + t)
-// so the classification pass is coalesced.
+// Alias tables.  The reference's stack algorithm is order dependent, so the pairing loop stays
+// sequential per word type; types are independent.  A warp takes 32 types at a time:
+//   phase A (cooperative, coalesced): for each of the 32 types the lanes stream the Phi^T row, form the
+//            normaliser (lane-strided fp64 partial sums + xor butterfly), classify every topic as "low"
+//            (b < 0) or "high" and compact the indices, in topic order, into the type's two stacks
+//            (ballot + popc prefix) -- the same stacks the sequential classification would build;
+//   phase B (one lane per type): the sequential pairing loop on the type's private scratch
+//            (b[K] fp64, one int stack[K]: "low" from the front, "high" from the back; both are popped
+//            in decreasing order, so the loop walks its own 12 K bytes with sector reuse).
+// Only the types that occur in this rank's tokens get a table (no token ever reads the others).
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 alias_build_kernel(Dims dm, const float *__restrict__ alpha, const float *__restrict__ phiT,
                    float *__restrict__ ps, int32_t *__restrict__ al, float *__restrict__ type_norm,
-                   double *__restrict__ bs, int32_t *__restrict__ stack)
+                   double *__restrict__ bs_all, int32_t *__restrict__ stack_all,
+                   const int32_t *__restrict__ active, int32_t n_active)
 {
+    const int lane = threadIdx.x & 31;
     const int64_t T = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t warp_first = tid - lane;          // scratch slot of lane 0 of this warp
     const int K = dm.K;
     const double k1 = 1.0 / (double)K;
-    for (int64_t w = tid; w < dm.V; w += T) {
-        const float *ph = phiT + (size_t)w * dm.Ks;
-        float *pw = ps + (size_t)w * dm.Ks;
-        int32_t *aw = al + (size_t)w * dm.Ks;
-        double norm = 0.0;
-        for (int k = 0; k < K; ++k) norm = __dadd_rn(norm, (double)__fmul_rn(alpha[k], ph[k]));
-        type_norm[w] = __double2float_rn(norm);
-        int low = 0, high = 0;   // low stack: stack[0..low), high stack: stack[K-high..K) (top = K-high)
-        for (int i = 0; i < K; ++i) {
-            aw[i] = i;
-            pw[i] = 0.0f;
-            const double b = __dsub_rn(__ddiv_rn((double)__fmul_rn(alpha[i], ph[i]), norm), k1);
-            bs[(size_t)i * T + tid] = b;
-            if (b < 0.0) stack[(size_t)(low++) * T + tid] = i;
-            else stack[(size_t)(K - 1 - (high++)) * T + tid] = i;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int64_t base = warp_first; base < n_active; base += T) {
+        int mylow = 0, myhigh = 0;
+        // ---- phase A
+        for (int j = 0; j < 32; ++j) {
+            if (base + j >= n_active) break;
+            const int64_t w = active[base + j];
+            const float *ph = phiT + (size_t)w * dm.Ks;
+            float *pw = ps + (size_t)w * dm.Ks;
+            int32_t *aw = al + (size_t)w * dm.Ks;
+            double *bs = bs_all + (size_t)(warp_first + j) * K;
+            int32_t *stack = stack_all + (size_t)(warp_first + j) * K;
+            double acc = 0.0;
+            for (int k = lane; k < K; k += 32) acc = __dadd_rn(acc, (double)__fmul_rn(alpha[k], ph[k]));
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(FULL, acc, off));
+            const double norm = acc;
+            if (lane == 0) type_norm[w] = __double2float_rn(norm);
+            int low = 0, high = 0;
+            for (int c0 = 0; c0 < K; c0 += 32) {
+                const int i = c0 + lane;
+                const bool valid = i < K;
+                double b = 0.0;
+                if (valid) {
+                    b = __dsub_rn(__ddiv_rn((double)__fmul_rn(alpha[i], ph[i]), norm), k1);
+                    bs[i] = b;
+                    aw[i] = i;
+                    pw[i] = 0.0f;
+                }
+                const bool is_low = valid && b < 0.0;
+                const unsigned lm = __ballot_sync(FULL, is_low), hm = __ballot_sync(FULL, valid && !is_low);
+                if (is_low) stack[low + __popc(lm & lt_mask)] = i;
+                else if (valid) stack[K - 1 - (high + __popc(hm & lt_mask))] = i;
+                low += __popc(lm);
+                high += __popc(hm);
+            }
+            if (lane == j) { mylow = low; myhigh = high; }
         }
-        while (low > 0 && high > 0) {
-            const int l = stack[(size_t)(--low) * T + tid];
-            const int h = stack[(size_t)(K - high) * T + tid];
-            const double c = bs[(size_t)l * T + tid], d = bs[(size_t)h * T + tid];
-            const double nb = __dadd_rn(c, d);
-            bs[(size_t)l * T + tid] = 0.0;
-            bs[(size_t)h * T + tid] = nb;
-            if (nb <= 0.0) high--;
-            if (nb < 0.0) stack[(size_t)(low++) * T + tid] = h;
-            aw[l] = h;
-            pw[l] = __double2float_rn(__dadd_rn(1.0, __dmul_rn((double)K, c)));
+        __syncwarp();
+        // ---- phase B
+        if (base + lane < n_active) {
+            const int64_t w = active[base + lane];
+            float *pw = ps + (size_t)w * dm.Ks;
+            int32_t *aw = al + (size_t)w * dm.Ks;
+            double *bs = bs_all + (size_t)tid * K;
+            int32_t *stack = stack_all + (size_t)tid * K;
+            // low stack: stack[0..low), high stack: stack[K-high..K) (top = K-high).  The reference loop
+            //   while (low>0 && high>0) { l = pop low; h = top high; b[h] += b[l]; b[l] = 0;
+            //                             if (b[h] <= 0) pop high; if (b[h] < 0) push h on low; a[l] = h; ps[l] = 1 + K c }
+            // with the two values it keeps re-reading held in registers: the residual of the current top
+            // high, and a high that just turned low (it is pushed on top of the low stack, so it is the
+            // next one popped).  b[] is then read once per topic and never written back.
+            int low = mylow, high = myhigh, h = 0, pl = 0;
+            double d = 0.0, pc = 0.0;
+            bool have_h = false, pending = false;
+            while ((pending || low > 0) && high > 0) {
+                int l;
+                double c;
+                if (pending) { l = pl; c = pc; pending = false; }
+                else { l = stack[--low]; c = bs[l]; }
+                if (!have_h) { h = stack[K - high]; d = bs[h]; have_h = true; }
+                const double nb = __dadd_rn(c, d);
+                d = nb;
+                if (nb <= 0.0) { high--; have_h = false; }
+                if (nb < 0.0) { pending = true; pl = h; pc = nb; }
+                aw[l] = h;
+                pw[l] = __double2float_rn(__dadd_rn(1.0, __dmul_rn((double)K, c)));
+            }
         }
+        __syncwarp();
     }
 }
 
 int64_t alias_scratch_threads(const Dims &dm, int sm_count)
 {
-    int64_t t = (int64_t)sm_count * 256;
+    int64_t t = (int64_t)sm_count * 512;
     int64_t need = ((int64_t)dm.V + 127) / 128 * 128;
     return need < t ? need : t;
 }
 
 cudaError_t launch_alias_build(const Dims &dm, const float *alpha, const float *phiT, float *ps, int32_t *al,
-                               float *type_norm, double *bs_scratch, int32_t *stack_scratch, int sm_count,
-                               cudaStream_t st)
+                               float *type_norm, double *bs_scratch, int32_t *stack_scratch,
+                               const int32_t *active, int32_t n_active, int sm_count, cudaStream_t st)
 {
+    if (n_active == 0) return cudaSuccess;
     const int64_t T = alias_scratch_threads(dm, sm_count);
-    alias_build_kernel<<<(unsigned)(T / 128), 128, 0, st>>>(dm, alpha, phiT, ps, al, type_norm, bs_scratch, stack_scratch);
+    // balanced rounds: when the types do not fit one wave of T threads, split them evenly over the rounds
+    const int64_t rounds = ((int64_t)n_active + T - 1) / T;
+    int64_t blocks = (((int64_t)n_active + rounds - 1) / rounds + 127) / 128;
+    if (blocks > T / 128) blocks = T / 128;
+    alias_build_kernel<<<(unsigned)blocks, 128, 0, st>>>(dm, alpha, phiT, ps, al, type_norm, bs_scratch,
+                                                       stack_scratch, active, n_active);
     return cudaGetLastError();
 }
+
 
 // ---------------------------------------------------------------------------------------
 // Sparse z-step.  One warp per document (PCGS is sequential inside a document).  The document's
@@ -90,7 +147,8 @@ struct SparseArgs {
     const float *ps;
     const int32_t *al;
     const float *type_norm;
-    int cap;   // list capacity per warp (multiple of 32)
+    int *lists;   // per resident warp: nz[cap], cnt[cap], cum[cap] in global memory (L1/L2 resident)
+    int cap;      // list capacity per warp (multiple of 32)
 };
 
 __device__ __forceinline__ int list_find(const int *nz, int nnz, int k, int lane)
@@ -105,11 +163,11 @@ __device__ __forceinline__ int list_find(const int *nz, int nnz, int k, int lane
 
 __global__ void __launch_bounds__(256) z_spalias_kernel(SparseArgs sa)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     const ZArgs &a = sa.z;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int K = a.dm.K, Ks = a.dm.Ks, cap = sa.cap;
-    int *nz = reinterpret_cast<int *>(smem_raw) + (size_t)warp * cap * 3;
+    // the lists are private to the warp; __syncwarp() orders lane 0's updates before the other lanes' reads
+    int *nz = sa.lists + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * (size_t)cap * 3;
     int *cnt = nz + cap;
     float *cum = reinterpret_cast<float *>(cnt + cap);
 
@@ -170,17 +228,30 @@ __global__ void __launch_bounds__(256) z_spalias_kernel(SparseArgs sa)
                 }
                 // sparse cumulative sum over the list (:178-191), chunks of 32 with sequential carries
                 float carry = 0.0f;
-                for (int c0 = 0; c0 < nnz; c0 += 32) {
-                    const int i = c0 + lane;
-                    float x = i < nnz ? __fmul_rn(__int2float_rn(cnt[i]), __ldg(ph + nz[i])) : 0.0f;
+                for (int g0 = 0; g0 < nnz; g0 += 128) {
+                    // four chunks at a time: all gathers are issued before the first scan needs one
+                    float xs[4];
 #pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) {
-                        const float y = __shfl_up_sync(FULL, x, off);
-                        if (lane >= off) x = __fadd_rn(x, y);
+                    for (int c = 0; c < 4; ++c) {
+                        const int i = g0 + 32 * c + lane;
+                        xs[c] = i < nnz ? __fmul_rn(__int2float_rn(cnt[i]), __ldg(ph + nz[i])) : 0.0f;
                     }
-                    const float cv = c0 == 0 ? x : __fadd_rn(carry, x);
-                    if (i < nnz) cum[i] = cv;
-                    carry = __shfl_sync(FULL, cv, 31);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int c0 = g0 + 32 * c;
+                        if (c0 < nnz) {
+                            const int i = c0 + lane;
+                            float x = xs[c];
+#pragma unroll
+                            for (int off = 1; off < 32; off <<= 1) {
+                                const float y = __shfl_up_sync(FULL, x, off);
+                                if (lane >= off) x = __fadd_rn(x, y);
+                            }
+                            const float cv = c0 == 0 ? x : __fadd_rn(carry, x);
+                            if (i < nnz) cum[i] = cv;
+                            carry = __shfl_sync(FULL, cv, 31);
+                        }
+                    }
                 }
                 __syncwarp();
                 const float sum = carry;
@@ -227,30 +298,30 @@ __global__ void __launch_bounds__(256) z_spalias_kernel(SparseArgs sa)
     }
 }
 
+size_t spalias_list_bytes(const Dims &dm, int max_doc_len, int sm_count)
+{
+    int cap = max_doc_len < dm.K ? max_doc_len : dm.K;
+    cap = (cap + 32 + 31) / 32 * 32;
+    return (size_t)sm_count * 8 * 8 * (size_t)cap * 12;   // up to 8 CTAs of 8 warps per SM
+}
+
 cudaError_t launch_z_spalias(const ZArgs &z, const float *ps, const int32_t *al, const float *type_norm,
-                             int max_doc_len, int sm_count, cudaStream_t st)
+                             int *lists, int max_doc_len, int sm_count, cudaStream_t st)
 {
     if (z.n_items == 0) return cudaSuccess;
     SparseArgs sa;
-    sa.z = z; sa.ps = ps; sa.al = al; sa.type_norm = type_norm;
+    sa.z = z; sa.ps = ps; sa.al = al; sa.type_norm = type_norm; sa.lists = lists;
     int cap = max_doc_len < z.dm.K ? max_doc_len : z.dm.K;
-    cap = (cap + 32 + 31) / 32 * 32;
-    sa.cap = cap;
-    const size_t per_warp = (size_t)cap * 12;
-    int warps = (int)((size_t)(200 * 1024) / per_warp);
-    if (warps < 1) return cudaErrorInvalidValue;   // a document with > ~17 000 distinct topics
-    if (warps > 8) warps = 8;
-    const size_t smem = warps * per_warp;
-    cudaError_t e = cudaFuncSetAttribute(z_spalias_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    sa.cap = (cap + 32 + 31) / 32 * 32;
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, z_spalias_kernel, warps * 32, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, z_spalias_kernel, 256, 0);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
     int64_t grid = (int64_t)sm_count * per_sm;
-    const int64_t need = (z.n_items + warps - 1) / warps;
+    const int64_t need = (z.n_items + 7) / 8;
     if (need < grid) grid = need;
-    z_spalias_kernel<<<(unsigned)grid, warps * 32, smem, st>>>(sa);
+    z_spalias_kernel<<<(unsigned)grid, 256, 0, st>>>(sa);
     return cudaGetLastError();
 }
 

@@ -21,13 +21,23 @@
 #include "lda_oracle.h"
 
 /* util/OptimizedGentleAliasMethod.java:52-79, in the precision the contract fixes:
- * pi_k = alpha_k * phi_k (fp32 product), normaliser = sequential fp64 sum of the products,
+ * pi_k = alpha_k * phi_k (fp32 product), normaliser = fp64 sum of the products (32 strided partial sums + butterfly),
  * b_i = pi_i / norm - 1/K in fp64, stack algorithm as written, ps stored as fp32. */
 static void alias_build_contract(int32_t K, const float *alpha_f, const float *phirow, float *ps,
                                  int32_t *al, float *type_norm, double *bs, int32_t *lows, int32_t *highs)
 {
-    double norm = 0.0;
-    for (int k = 0; k < K; ++k) norm = norm + (double)(alpha_f[k] * phirow[k]);
+    /* normaliser: 32 strided fp64 partial sums (lane l takes topics l, l+32, ...), xor butterfly */
+    double acc[32], tmp[32];
+    for (int l = 0; l < 32; ++l) {
+        double s = 0.0;
+        for (int k = l; k < K; k += 32) s = s + (double)(alpha_f[k] * phirow[k]);
+        acc[l] = s;
+    }
+    for (int off = 16; off >= 1; off >>= 1) {
+        for (int l = 0; l < 32; ++l) tmp[l] = acc[l] + acc[l ^ off];
+        memcpy(acc, tmp, sizeof acc);
+    }
+    const double norm = acc[0];
     *type_norm = (float)norm;
     int low = 0, high = 0;
     const double k1 = 1.0 / (double)K;
