@@ -24,7 +24,8 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl")
     ok = True
-    for scheme, osch, K, V in (("gpu_ggs", O.GGS, 100, 900), ("gpu_pcgs", O.PCGS, 400, 1300), ("gpu_ggs", O.GGS, 1000, 2100)):
+    for scheme, osch, K, V in (("gpu_ggs", O.GGS, 100, 900), ("gpu_pcgs", O.PCGS, 400, 1300), ("gpu_ggs", O.GGS, 1000, 2100),
+                               ("gpu_spalias", O.SPALIAS, 1500, 700)):
         alpha, beta, seed = 50.0 / K, 0.01, 2019
         off, tokens = L.synth_corpus(400, V, 70.0, seed=8)
         cfg = L.LDAConfiguration(scheme=scheme, topics=K, alpha=alpha, beta=beta, seed=seed, exec_time=0)
