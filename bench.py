@@ -197,13 +197,12 @@ def main():
                 vals.append(r)
         v = float(np.mean([x["value"] for x in vals]))
         cb = dict(vals[-1]); cb["value"] = v
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": args.warmup,
-                          "ms_per_step": 1e3 * n_shard / v, "higher_is_better": True, "scaling": "weak",
-                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                          "cpu_baseline": cb,
-                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-        return
+        return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * n_shard / v, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": cb,
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
     # ----------------------------------------------------------------------------------------
     import torch
@@ -338,12 +337,23 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(wl, off, tokens, args.cpu_sample_tokens, n_total)
     s.close()
-    if rank == 0:
-        print(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return out if rank == 0 else None
 
 
 if __name__ == "__main__":
-    main()
+    # Libraries (NCCL's version banner, for one) write to the process's stdout; the contract is ONE JSON
+    # line there.  Point fd 1 at stderr while the benchmark runs and restore it for the result.
+    sys.stdout.flush()
+    _saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        _result = main()
+    finally:
+        sys.stdout.flush()
+        os.dup2(_saved_stdout, 1)
+        os.close(_saved_stdout)
+    if _result is not None:
+        print(json.dumps(_result), flush=True)
