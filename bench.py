@@ -323,7 +323,8 @@ def main():
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": dict(config, tokens_total=n_total, tokens_per_gpu=sizes, corpus_gen_s=round(gen_s, 1),
+           "config": dict(config, exchange=s.getExchangeMode(), tokens_total=n_total, tokens_per_gpu=sizes,
+                          corpus_gen_s=round(gen_s, 1),
                           wall_ms_per_step=wall_ms / args.steps),
            "clocks": ck,
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n_local,

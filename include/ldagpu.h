@@ -66,6 +66,12 @@ int ldagpu_destroy(ldagpu_handle h);
  * one reduce-scatter and Phi with one all-gather per sweep. */
 int ldagpu_comm_unique_id(void *id128);
 int ldagpu_comm_init(ldagpu_handle h, int32_t rank, int32_t world, const void *id128);
+/* how the ranks exchange counts and Phi: 0 = single GPU, 1 = NCCL collectives (reduce-scatter / all-gather
+ * around the Phi kernels), 2 = peer memory (default when the GPUs have peer access: the Phi kernels load the
+ * other ranks' partial counts and store Phi into every rank's copy over NVLink themselves).  Environment:
+ * LDAGPU_EXCHANGE=nccl|p2p forces one; LDAGPU_P2P_TIMEOUT_MS bounds a wait on a dead rank (default 20000).
+ * The stand-in for the reference's shared AtomicInteger[K][V] delta matrix (UPL:102,363-368,1107-1221). */
+int ldagpu_get_exchange_mode(ldagpu_handle h, int32_t *mode);
 
 /* initial z = MALLET Randoms(seed).nextInt(K) in document order (UPL:398-406,458-460; MSL:153-156).
  * skip = number of draws consumed by the shards before this one (token_base on a sharded corpus).

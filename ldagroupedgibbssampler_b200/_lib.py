@@ -13,7 +13,7 @@ SO_PATH = os.environ.get("LDAGPU_LIBRARY") or os.path.join(_HERE, "libldagpu.so"
 # every entry point include/ldagpu.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "ldagpu_version", "ldagpu_last_error", "ldagpu_device_count", "ldagpu_create", "ldagpu_destroy",
-    "ldagpu_comm_unique_id", "ldagpu_comm_init", "ldagpu_init_z_java_random", "ldagpu_set_z",
+    "ldagpu_comm_unique_id", "ldagpu_comm_init", "ldagpu_get_exchange_mode", "ldagpu_init_z_java_random", "ldagpu_set_z",
     "ldagpu_get_z", "ldagpu_sweep", "ldagpu_sample_z_given_phi", "ldagpu_next_iteration",
     "ldagpu_sample_theta", "ldagpu_sample_z", "ldagpu_rebuild_counts", "ldagpu_sample_phi",
     "ldagpu_get_iteration", "ldagpu_set_iteration", "ldagpu_get_type_topic_counts",
@@ -65,6 +65,7 @@ def load() -> C.CDLL:
               "ldagpu_sample_phi", "ldagpu_abort"):
         sig(n, C.c_int, vp)
     sig("ldagpu_get_iteration", C.c_int, vp, pi32)
+    sig("ldagpu_get_exchange_mode", C.c_int, vp, pi32)
     sig("ldagpu_set_iteration", C.c_int, vp, i32)
     for n in ("ldagpu_get_type_topic_counts", "ldagpu_get_topic_totals", "ldagpu_get_doc_topic_counts",
               "ldagpu_get_phi", "ldagpu_set_phi", "ldagpu_get_theta", "ldagpu_set_theta"):

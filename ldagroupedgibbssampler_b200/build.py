@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 OUT = os.path.join(HERE, "libldagpu.so")
 
-CU = ["kernels_z.cu", "kernels_z_big.cu", "kernels_sparse.cu", "kernels_phi.cu", "kernels_misc.cu", "engine.cu"]
+CU = ["kernels_z.cu", "kernels_z_big.cu", "kernels_sparse.cu", "kernels_phi.cu", "kernels_p2p.cu", "kernels_misc.cu", "engine.cu"]
 CPP = ["synth.cpp"]
 HEADERS = ["common.cuh", "contract_math.cuh", os.path.join("..", "..", "include", "ldagpu.h")]
 

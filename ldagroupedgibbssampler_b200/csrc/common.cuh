@@ -51,6 +51,45 @@ struct ThetaArgs {
     uint32_t seed_lo, seed_hi, sweep;
 };
 
+// ---------------------------------------------------------------------------------------
+// Peer-memory exchange (kernels_p2p.cu, kernels_phi.cu): one process per GPU; every rank maps the
+// other ranks' buffers with CUDA IPC, and the count exchange / Phi broadcast of a sweep are loads
+// and stores over NVLink inside the Phi kernels instead of collectives around them.
+// ---------------------------------------------------------------------------------------
+constexpr int P2P_MAX = 8;           // ranks of one NVSwitch box (= PHI_SEGMENTS)
+enum : int { P2P_FLAG_COUNTS = 0, P2P_FLAG_SEG = 1, P2P_FLAG_PHI = 2, P2P_FLAG_BAR = 3, P2P_FLAG_KINDS = 4 };
+
+struct PeerTable {
+    int32_t *n_wk[P2P_MAX];      // [Vp][Ks] partial counts of every rank (own entry = local buffer)
+    float *phiT[P2P_MAX];        // [Vp][Ks] replicated Phi^T of every rank
+    double *seg[P2P_MAX];        // [PHI_SEGMENTS][Ks] segment sums of every rank
+    int32_t *nk_parts[P2P_MAX];  // [P2P_MAX][Ks] per-source topic totals landing on every rank
+    uint32_t *flags[P2P_MAX];    // [P2P_FLAG_KINDS][P2P_MAX] epoch written by source rank, on every rank
+    uint32_t *done_ctr;          // local: [P2P_FLAG_KINDS] CTA completion counters ("last block signals")
+    int *error;                  // local: set when a wait timed out
+    unsigned long long timeout_ns;
+    int rank, world;
+};
+
+// n_k parts to every rank + "my partial counts are complete" (epoch) to every rank
+cudaError_t launch_p2p_push_topic_totals(const PeerTable &pt, const int32_t *n_k_local, int32_t Ks, uint32_t epoch,
+                                         cudaStream_t st);
+// stand-alone reduce of the rank's vocabulary rows over all ranks' partial counts (+ n_k from the parts)
+cudaError_t launch_p2p_reduce_counts(const PeerTable &pt, const Dims &dm, int32_t *n_k, int32_t row0, int32_t row1,
+                                     uint32_t epoch, int sm_count, cudaStream_t st);
+// signal `kind` with `epoch` to every rank / wait until every rank has signalled it
+cudaError_t launch_p2p_signal(const PeerTable &pt, int kind, uint32_t epoch, cudaStream_t st);
+cudaError_t launch_p2p_wait(const PeerTable &pt, int kind, uint32_t epoch, cudaStream_t st);
+// fused variants of the three Phi kernels (kernels_phi.cu)
+cudaError_t launch_phi_draw_p2p(const PeerTable &pt, bool reduce_counts, uint32_t epoch_counts, const Dims &dm,
+                                int32_t *n_wk, int32_t *n_k, double beta, float *phiT, double *partial, int32_t row0,
+                                int32_t row1, uint32_t seed_lo, uint32_t seed_hi, uint32_t sweep, cudaStream_t st);
+cudaError_t launch_phi_segment_sums_p2p(const PeerTable &pt, uint32_t epoch_seg, const Dims &dm, const double *partial,
+                                        int seg0, int seg1, cudaStream_t st);
+cudaError_t launch_phi_normalise_p2p(const PeerTable &pt, uint32_t epoch_seg, uint32_t epoch_phi, const Dims &dm,
+                                     double *topic_sum, double *phi_mean_sum, int32_t row0, int32_t row1,
+                                     cudaStream_t st);
+
 // launchers (each returns the cudaError of the launch)
 cudaError_t launch_theta(const ThetaArgs &a, int sm_count, cudaStream_t st);
 cudaError_t launch_z_ggs(const ZArgs &a, int sm_count, cudaStream_t st);
@@ -153,6 +192,62 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
             smem_u32(dst)),
         "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+}
+
+// ---- cross-GPU flags: release/acquire at system scope over peer-mapped memory ----------------
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// One thread: spin until every rank's flag of `kind` (in THIS rank's flag array) has reached epoch.
+// A rank that never arrives (dead peer process) must not hang the GPU: after timeout_ns the wait
+// gives up and raises the error word, which the host checks after every synchronise.
+__device__ __forceinline__ void p2p_wait_all(const PeerTable &pt, int kind, uint32_t epoch)
+{
+    const uint32_t *f = pt.flags[pt.rank] + kind * P2P_MAX;
+    const unsigned long long t0 = globaltimer_ns();
+    for (int r = 0; r < pt.world; ++r) {
+        // epochs only grow; the signed difference keeps the comparison valid across a wrap
+        while ((int32_t)(ld_acquire_sys(f + r) - epoch) < 0) {
+            if (globaltimer_ns() - t0 > pt.timeout_ns) { atomicExch(pt.error, 1 + kind); return; }
+            __nanosleep(200);
+        }
+    }
+}
+// One thread per destination rank (tid < world): publish epoch in every rank's flag array.
+__device__ __forceinline__ void p2p_signal_one(const PeerTable &pt, int kind, uint32_t epoch, int dst)
+{
+    st_release_sys(pt.flags[dst] + kind * P2P_MAX + pt.rank, epoch);
+}
+// "last block signals": every thread has finished its peer stores; the CTA that arrives last at the
+// local counter publishes the epoch to all ranks.
+__device__ __forceinline__ void p2p_cta_done_signal(const PeerTable &pt, int kind, uint32_t epoch, unsigned total_ctas)
+{
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(pt.done_ctr + kind, 1u);
+        s_last = prev == total_ctas - 1;
+        if (s_last) pt.done_ctr[kind] = 0;   // ready for the next launch (stream order separates launches)
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if ((int)threadIdx.x < pt.world) p2p_signal_one(pt, kind, epoch, (int)threadIdx.x);
+    }
 }
 #endif
 

@@ -11,6 +11,11 @@
 //   [G>1] all-gather the 8 segment sums
 //   phi_normalise             rows of the slice
 //   [G>1] all-gather Phi^T
+// With peer access between the GPUs (the default on an NVSwitch box) the three [G>1] steps are not
+// collectives: the Phi kernels load the peers' partial counts and store the segment sums and the
+// normalised rows into every rank's buffers themselves (kernels_p2p.cu, kernels_phi.cu); NCCL only
+// bootstraps (IPC handle exchange) and serves the accessors.  LDAGPU_EXCHANGE=nccl keeps the
+// collective path.
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -19,6 +24,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -144,6 +150,15 @@ struct ldagpu_handle_s {
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
     int32_t row0 = 0, row1 = 0, seg0 = 0, seg1 = PHI_SEGMENTS;
+    // peer-memory exchange
+    bool p2p = false;
+    PeerTable pt{};
+    DevBuf<int32_t> nk_parts;
+    DevBuf<uint32_t> p2p_flags, p2p_local;   // shared epoch flags; local {done counters[4], error}
+    std::vector<void *> ipc_opened;
+    uint32_t ep[P2P_FLAG_KINDS] = {0, 0, 0, 0};
+    uint32_t counts_epoch = 0;   // epoch of the last "counts complete" signal (consumed by the reduce)
+    std::string p2p_note;
 
     std::atomic<int> abort_flag{0};
     std::string err;
@@ -253,18 +268,67 @@ int step_counts_local(ldagpu_handle h)
     return 0;
 }
 
-int step_counts_exchange(ldagpu_handle h)
+// defer_reduce (peer-memory mode): only announce the partial counts; the Phi draw that follows sums them.
+int step_counts_exchange(ldagpu_handle h, bool defer_reduce)
 {
     if (h->world == 1) return 0;
+    if (h->p2p) {
+        h->counts_epoch = ++h->ep[P2P_FLAG_COUNTS];
+        CK(h, launch_p2p_push_topic_totals(h->pt, h->n_k.p, h->dm.Ks, h->counts_epoch, h->stream));
+        h->last_launches += 1;
+        if (defer_reduce) return 0;
+        CK(h, launch_p2p_reduce_counts(h->pt, h->dm, h->n_k.p, h->row0, h->row1, h->counts_epoch, h->sm_count, h->stream));
+        // nobody may touch its partial counts again before every rank has read them
+        const uint32_t e = ++h->ep[P2P_FLAG_BAR];
+        CK(h, launch_p2p_signal(h->pt, P2P_FLAG_BAR, e, h->stream));
+        CK(h, launch_p2p_wait(h->pt, P2P_FLAG_BAR, e, h->stream));
+        h->last_launches += 3;
+        return 0;
+    }
     const size_t slice = (size_t)(h->dm.Vp / h->world) * h->dm.Ks;
     NK(h, g_nccl.ReduceScatter(h->n_wk.p, h->n_wk.p + (size_t)h->rank * slice, slice, ncclInt32, ncclSum, h->comm, h->stream));
     NK(h, g_nccl.AllReduce(h->n_k.p, h->n_k.p, (size_t)h->dm.Ks, ncclInt32, ncclSum, h->comm, h->stream));
     return 0;
 }
 
-// ev != nullptr: record events after draw+segments, segment all-gather, normalise, Phi all-gather
-int step_phi(ldagpu_handle h, bool accumulate_mean, cudaEvent_t *ev)
+int phi_mean_buffer(ldagpu_handle h, bool accumulate_mean, double **mean)
 {
+    *mean = nullptr;
+    if (!accumulate_mean) return 0;
+    if (!h->phi_mean.p) {
+        CK(h, h->phi_mean.alloc((size_t)h->dm.Vp * h->dm.Ks));
+        CK(h, cudaMemsetAsync(h->phi_mean.p, 0, sizeof(double) * h->phi_mean.n, h->stream));
+    }
+    *mean = h->phi_mean.p;
+    return 0;
+}
+
+// peer-memory mode: draw (summing the peers' partial counts when fused_reduce), segment sums stored to
+// every rank, normalise + store the rows to every rank, wait until every rank's rows have landed here
+int step_phi_p2p(ldagpu_handle h, bool accumulate_mean, cudaEvent_t *ev, bool fused_reduce)
+{
+    const uint32_t lo = (uint32_t)h->seed, hi = (uint32_t)(h->seed >> 32);
+    CK(h, launch_phi_draw_p2p(h->pt, fused_reduce, h->counts_epoch, h->dm, h->n_wk.p, h->n_k.p, h->beta, h->phiT.p,
+                              h->partial.p, h->row0, h->row1, lo, hi, (uint32_t)h->iteration, h->stream));
+    const uint32_t e_seg = ++h->ep[P2P_FLAG_SEG];
+    CK(h, launch_phi_segment_sums_p2p(h->pt, e_seg, h->dm, h->partial.p, h->seg0, h->seg1, h->stream));
+    if (ev) { CK(h, cudaEventRecord(ev[0], h->stream)); CK(h, cudaEventRecord(ev[1], h->stream)); }
+    double *mean = nullptr;
+    if (phi_mean_buffer(h, accumulate_mean, &mean)) return 1;
+    const uint32_t e_phi = ++h->ep[P2P_FLAG_PHI];
+    CK(h, launch_phi_normalise_p2p(h->pt, e_seg, e_phi, h->dm, h->topic_sum.p, mean, h->row0, h->row1, h->stream));
+    if (ev) CK(h, cudaEventRecord(ev[2], h->stream));
+    CK(h, launch_p2p_wait(h->pt, P2P_FLAG_PHI, e_phi, h->stream));
+    h->last_launches += 4;
+    if (step_alias(h)) return 1;
+    if (ev) CK(h, cudaEventRecord(ev[3], h->stream));
+    return 0;
+}
+
+// ev != nullptr: record events after draw+segments, segment all-gather, normalise, Phi all-gather
+int step_phi(ldagpu_handle h, bool accumulate_mean, cudaEvent_t *ev, bool fused_reduce = false)
+{
+    if (h->p2p) return step_phi_p2p(h, accumulate_mean, ev, fused_reduce);
     const uint32_t lo = (uint32_t)h->seed, hi = (uint32_t)(h->seed >> 32);
     CK(h, launch_phi_draw(h->dm, h->n_wk.p, h->beta, h->phiT.p, h->partial.p, h->row0, h->row1, lo, hi,
                           (uint32_t)h->iteration, h->stream));
@@ -277,13 +341,7 @@ int step_phi(ldagpu_handle h, bool accumulate_mean, cudaEvent_t *ev)
     }
     if (ev) CK(h, cudaEventRecord(ev[1], h->stream));
     double *mean = nullptr;
-    if (accumulate_mean) {
-        if (!h->phi_mean.p) {
-            CK(h, h->phi_mean.alloc((size_t)h->dm.Vp * h->dm.Ks));
-            CK(h, cudaMemsetAsync(h->phi_mean.p, 0, sizeof(double) * h->phi_mean.n, h->stream));
-        }
-        mean = h->phi_mean.p;
-    }
+    if (phi_mean_buffer(h, accumulate_mean, &mean)) return 1;
     CK(h, launch_phi_normalise(h->dm, h->seg.p, h->topic_sum.p, h->phiT.p, mean, h->row0, h->row1, h->stream));
     h->last_launches += 1;
     if (ev) CK(h, cudaEventRecord(ev[2], h->stream));
@@ -307,6 +365,15 @@ int sync_check(ldagpu_handle h)
 {
     CK(h, cudaStreamSynchronize(h->stream));
     CK(h, cudaGetLastError());
+    if (h->p2p) {
+        int err = 0;
+        CK(h, cudaMemcpy(&err, h->p2p_local.p + P2P_FLAG_KINDS, sizeof err, cudaMemcpyDeviceToHost));
+        if (err) {
+            static const char *what[] = {"partial counts", "segment sums", "Phi rows", "barrier"};
+            return h->fail("peer-memory exchange: waiting for the %s of another rank timed out (is a rank dead?)",
+                           what[(err - 1) & 3]);
+        }
+    }
     return 0;
 }
 
@@ -331,11 +398,11 @@ int run_sweeps(ldagpu_handle h, int32_t n, bool with_phi, int32_t *done)
         CK(h, launch_topic_totals(h->dm, h->n_wk.p, h->n_k.p, h->stream));
         h->last_launches += 1;
         CK(h, cudaEventRecord(ev[3], h->stream));
-        if (step_counts_exchange(h)) return 1;
+        if (step_counts_exchange(h, with_phi)) return 1;
         CK(h, cudaEventRecord(ev[4], h->stream));
         if (with_phi) {
             bool acc = mean_this_iteration(h);
-            if (step_phi(h, acc, ev + 5)) return 1;
+            if (step_phi(h, acc, ev + 5, true)) return 1;
             if (acc) h->n_sampled_phi += 1;   // GGS:168-170
         } else {
             for (int i = 5; i < EV_PER_SWEEP; ++i) CK(h, cudaEventRecord(ev[i], h->stream));
@@ -403,6 +470,104 @@ int validate_z(ldagpu_handle h)
     CK(h, cudaMemcpyAsync(&bad, h->bad.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     if (bad) return h->fail("topic indicator out of range [0, %d)", h->dm.K);   // UPL:475-481 throws
+    return 0;
+}
+
+// Peer-memory exchange: map every other rank's n_wk / Phi^T / segment sums / n_k parts / flags with
+// CUDA IPC (handles travel through one NCCL all-gather).  All ranks agree on the outcome; when a mapping
+// fails (no peer access, IPC disabled) or LDAGPU_EXCHANGE=nccl, the NCCL collectives stay in charge.
+struct IpcBlob {
+    cudaIpcMemHandle_t n_wk, phiT, seg, nk_parts, flags;
+};
+
+void close_peer_exchange(ldagpu_handle h)
+{
+    for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+    h->ipc_opened.clear();
+    h->p2p = false;
+}
+
+int setup_peer_exchange(ldagpu_handle h)
+{
+    const char *mode = getenv("LDAGPU_EXCHANGE");
+    const bool want = !(mode && std::strcmp(mode, "nccl") == 0);
+    const int G = h->world;
+    CK(h, h->nk_parts.alloc((size_t)P2P_MAX * h->dm.Ks));
+    CK(h, h->p2p_flags.alloc((size_t)P2P_FLAG_KINDS * P2P_MAX));
+    CK(h, h->p2p_local.alloc((size_t)P2P_FLAG_KINDS + 4));
+    CK(h, cudaMemset(h->nk_parts.p, 0, sizeof(int32_t) * h->nk_parts.n));
+    CK(h, cudaMemset(h->p2p_flags.p, 0, sizeof(uint32_t) * h->p2p_flags.n));
+    CK(h, cudaMemset(h->p2p_local.p, 0, sizeof(uint32_t) * h->p2p_local.n));
+
+    int ok = want && G <= P2P_MAX ? 1 : 0;
+    if (!want) h->p2p_note = "LDAGPU_EXCHANGE=nccl";
+    IpcBlob mine{};
+    if (ok) {
+        cudaError_t e = cudaIpcGetMemHandle(&mine.n_wk, h->n_wk.p);
+        if (e == cudaSuccess) e = cudaIpcGetMemHandle(&mine.phiT, h->phiT.p);
+        if (e == cudaSuccess) e = cudaIpcGetMemHandle(&mine.seg, h->seg.p);
+        if (e == cudaSuccess) e = cudaIpcGetMemHandle(&mine.nk_parts, h->nk_parts.p);
+        if (e == cudaSuccess) e = cudaIpcGetMemHandle(&mine.flags, h->p2p_flags.p);
+        if (e != cudaSuccess) { ok = 0; h->p2p_note = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e); cudaGetLastError(); }
+    }
+    // all-gather the handles (as bytes) and every rank's device ordinal
+    DevBuf<unsigned char> blobs;
+    CK(h, blobs.alloc(sizeof(IpcBlob) * (size_t)G));
+    CK(h, cudaMemcpyAsync(blobs.p + sizeof(IpcBlob) * (size_t)h->rank, &mine, sizeof mine, cudaMemcpyHostToDevice, h->stream));
+    NK(h, g_nccl.AllGather(blobs.p + sizeof(IpcBlob) * (size_t)h->rank, blobs.p, sizeof(IpcBlob), ncclChar, h->comm, h->stream));
+    std::vector<IpcBlob> all((size_t)G);
+    CK(h, cudaMemcpyAsync(all.data(), blobs.p, sizeof(IpcBlob) * (size_t)G, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    blobs.release();
+
+    PeerTable &pt = h->pt;
+    pt = PeerTable{};
+    pt.rank = h->rank; pt.world = G;
+    pt.done_ctr = h->p2p_local.p;
+    pt.error = reinterpret_cast<int *>(h->p2p_local.p + P2P_FLAG_KINDS);
+    const char *to = getenv("LDAGPU_P2P_TIMEOUT_MS");
+    pt.timeout_ns = (unsigned long long)(to ? std::max(1L, atol(to)) : 20000L) * 1000000ull;
+    if (ok) {
+        for (int r = 0; r < G && ok; ++r) {
+            if (r == h->rank) {
+                pt.n_wk[r] = h->n_wk.p; pt.phiT[r] = h->phiT.p; pt.seg[r] = h->seg.p;
+                pt.nk_parts[r] = h->nk_parts.p; pt.flags[r] = h->p2p_flags.p;
+                continue;
+            }
+            auto open = [&](const cudaIpcMemHandle_t &mh, void **out) {
+                cudaError_t e = cudaIpcOpenMemHandle(out, mh, cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) {
+                    ok = 0;
+                    h->p2p_note = std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(r) + "): " + cudaGetErrorString(e);
+                    cudaGetLastError();
+                    return;
+                }
+                h->ipc_opened.push_back(*out);
+            };
+            open(all[(size_t)r].n_wk, reinterpret_cast<void **>(&pt.n_wk[r]));
+            if (ok) open(all[(size_t)r].phiT, reinterpret_cast<void **>(&pt.phiT[r]));
+            if (ok) open(all[(size_t)r].seg, reinterpret_cast<void **>(&pt.seg[r]));
+            if (ok) open(all[(size_t)r].nk_parts, reinterpret_cast<void **>(&pt.nk_parts[r]));
+            if (ok) open(all[(size_t)r].flags, reinterpret_cast<void **>(&pt.flags[r]));
+        }
+    }
+    // every rank must take the same path
+    DevBuf<int> agree;
+    CK(h, agree.alloc(1));
+    CK(h, cudaMemcpyAsync(agree.p, &ok, sizeof ok, cudaMemcpyHostToDevice, h->stream));
+    NK(h, g_nccl.AllReduce(agree.p, agree.p, 1, ncclInt32, ncclMin, h->comm, h->stream));
+    int all_ok = 0;
+    CK(h, cudaMemcpyAsync(&all_ok, agree.p, sizeof all_ok, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    agree.release();
+    if (!all_ok) {
+        if (ok) h->p2p_note = "another rank could not map peer memory";
+        close_peer_exchange(h);
+        if (want && getenv("LDAGPU_EXCHANGE") && std::strcmp(getenv("LDAGPU_EXCHANGE"), "p2p") == 0)
+            return h->fail("LDAGPU_EXCHANGE=p2p but peer memory is unavailable: %s", h->p2p_note.c_str());
+        return 0;
+    }
+    h->p2p = true;
     return 0;
 }
 
@@ -555,7 +720,10 @@ int ldagpu_destroy(ldagpu_handle h)
     if (!h) return 0;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+    h->ipc_opened.clear();
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    h->nk_parts.release(); h->p2p_flags.release(); h->p2p_local.release();
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
     h->doc_off.release(); h->item_begin.release(); h->tokens.release(); h->z.release(); h->n_wk.release();
     h->n_k.release(); h->item_doc.release(); h->scratch_i32.release(); h->phiT.release(); h->theta.release();
@@ -607,13 +775,20 @@ int ldagpu_comm_init(ldagpu_handle h, int32_t rank, int32_t world, const void *i
     CK(h, cudaStreamSynchronize(h->stream));
     tmp.release();
     h->D_global = d;
+    return setup_peer_exchange(h);
+}
+
+int ldagpu_get_exchange_mode(ldagpu_handle h, int32_t *mode)
+{
+    if (!h || !mode) return 1;
+    *mode = h->world == 1 ? 0 : (h->p2p ? 2 : 1);
     return 0;
 }
 
 static int refresh_counts_and_phi(ldagpu_handle h, bool redraw_phi)
 {
-    if (step_counts_local(h) || step_counts_exchange(h)) return 1;
-    if (redraw_phi && step_phi(h, false, nullptr)) return 1;
+    if (step_counts_local(h) || step_counts_exchange(h, redraw_phi)) return 1;
+    if (redraw_phi && step_phi(h, false, nullptr, true)) return 1;
     return sync_check(h);
 }
 

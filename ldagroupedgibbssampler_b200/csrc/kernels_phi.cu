@@ -30,9 +30,17 @@ constexpr int PHI_THREADS = 128;
 // and drained by all threads, each taking the next entry when its cell is accepted.  Cells are keyed
 // by (w, k, attempt), so the evaluation order does not change any value; the column sums are taken
 // afterwards in row order.
+//
+// REDUCE (multi-GPU, peer memory): the counts of a cell are the sum of every rank's partial counts,
+// loaded straight from the peers' n_wk over NVLink while the CTA's previous/next neighbours are in
+// their Gamma loops -- the reduce-scatter of the sweep happens inside this kernel.  The global counts
+// are written back to the rank's own rows (accessors, log-likelihood), n_k comes from the per-rank
+// totals the peers pushed before they signalled.
+template <bool REDUCE>
 __global__ void __launch_bounds__(PHI_THREADS)
-phi_draw_kernel(Dims dm, const int32_t *__restrict__ n_wk, double beta, float *__restrict__ phiT,
-                double *__restrict__ partial, int32_t row0, uint32_t seed_lo, uint32_t seed_hi, uint32_t sweep)
+phi_draw_kernel(PeerTable pt, uint32_t epoch_counts, Dims dm, int32_t *n_wk, int32_t *n_k,
+                double beta, float *__restrict__ phiT, double *__restrict__ partial, int32_t row0, uint32_t seed_lo,
+                uint32_t seed_hi, uint32_t sweep)
 {
     __shared__ int32_t s_n[PHI_ROW_BLOCK][PHI_THREADS];
     __shared__ float s_g[PHI_ROW_BLOCK][PHI_THREADS];
@@ -43,12 +51,44 @@ phi_draw_kernel(Dims dm, const int32_t *__restrict__ n_wk, double beta, float *_
     const int32_t wb = row0 + blockIdx.x * PHI_ROW_BLOCK;
     const bool col_ok = k < dm.Ks;
     if (tid == 0) { s_count = 0; s_next = PHI_THREADS; }
-    // stage the 8 counts of this column with coalesced loads
+    if (REDUCE) {
+        if (tid == 0) p2p_wait_all(pt, P2P_FLAG_COUNTS, epoch_counts);   // every rank's z-step has finished
+        __syncthreads();
+        int32_t acc[PHI_ROW_BLOCK];
 #pragma unroll
-    for (int r = 0; r < PHI_ROW_BLOCK; ++r) {
-        int32_t w = wb + r;
-        s_n[r][tid] = (col_ok && w < dm.V) ? n_wk[(size_t)w * dm.Ks + k] : 0;
-        s_g[r][tid] = 0.0f;
+        for (int r = 0; r < PHI_ROW_BLOCK; ++r) acc[r] = 0;
+#pragma unroll
+        for (int q = 0; q < P2P_MAX; ++q) {
+            if (q < pt.world) {
+                const int32_t *src = pt.n_wk[q];
+#pragma unroll
+                for (int r = 0; r < PHI_ROW_BLOCK; ++r) {
+                    const int32_t w = wb + r;
+                    if (col_ok && w < dm.V) acc[r] += __ldcg(src + (size_t)w * dm.Ks + k);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < PHI_ROW_BLOCK; ++r) {
+            const int32_t w = wb + r;
+            s_n[r][tid] = acc[r];
+            s_g[r][tid] = 0.0f;
+            if (col_ok && w < dm.V) n_wk[(size_t)w * dm.Ks + k] = acc[r];
+        }
+        if (blockIdx.x == 0 && col_ok) {
+            const int32_t *parts = pt.nk_parts[pt.rank];
+            int32_t t = 0;
+            for (int q = 0; q < pt.world; ++q) t += __ldcg(parts + (size_t)q * dm.Ks + k);
+            n_k[k] = t;
+        }
+    } else {
+        // stage the 8 counts of this column with coalesced loads
+#pragma unroll
+        for (int r = 0; r < PHI_ROW_BLOCK; ++r) {
+            int32_t w = wb + r;
+            s_n[r][tid] = (col_ok && w < dm.V) ? n_wk[(size_t)w * dm.Ks + k] : 0;
+            s_g[r][tid] = 0.0f;
+        }
     }
     __syncthreads();
     bool boost0;
@@ -113,21 +153,46 @@ cudaError_t launch_phi_draw(const Dims &dm, const int32_t *n_wk, double beta, fl
 {
     if (row1 <= row0) return cudaSuccess;
     dim3 grid((row1 - row0) / PHI_ROW_BLOCK, (dm.Ks + PHI_THREADS - 1) / PHI_THREADS);
-    phi_draw_kernel<<<grid, PHI_THREADS, 0, st>>>(dm, n_wk, beta, phiT, partial, row0, seed_lo, seed_hi, sweep);
+    phi_draw_kernel<false><<<grid, PHI_THREADS, 0, st>>>(PeerTable{}, 0u, dm, const_cast<int32_t *>(n_wk), nullptr, beta,
+                                                         phiT, partial, row0, seed_lo, seed_hi, sweep);
     return cudaGetLastError();
 }
 
+cudaError_t launch_phi_draw_p2p(const PeerTable &pt, bool reduce_counts, uint32_t epoch_counts, const Dims &dm,
+                                int32_t *n_wk, int32_t *n_k, double beta, float *phiT, double *partial, int32_t row0,
+                                int32_t row1, uint32_t seed_lo, uint32_t seed_hi, uint32_t sweep, cudaStream_t st)
+{
+    if (!reduce_counts) return launch_phi_draw(dm, n_wk, beta, phiT, partial, row0, row1, seed_lo, seed_hi, sweep, st);
+    if (row1 <= row0) return cudaSuccess;
+    dim3 grid((row1 - row0) / PHI_ROW_BLOCK, (dm.Ks + PHI_THREADS - 1) / PHI_THREADS);
+    phi_draw_kernel<true><<<grid, PHI_THREADS, 0, st>>>(pt, epoch_counts, dm, n_wk, n_k, beta, phiT, partial, row0,
+                                                        seed_lo, seed_hi, sweep);
+    return cudaGetLastError();
+}
+
+// P2P: the rank's segment sums are stored into every rank's seg buffer (the all-gather of the 8 x Ks
+// doubles), and the last CTA publishes "segments of rank r are in place".
+template <bool P2P>
 __global__ void __launch_bounds__(PHI_THREADS)
-phi_segment_kernel(Dims dm, const double *__restrict__ partial, double *__restrict__ seg, int seg0)
+phi_segment_kernel(PeerTable pt, uint32_t epoch_seg, Dims dm, const double *__restrict__ partial,
+                   double *__restrict__ seg, int seg0)
 {
     const int k = blockIdx.x * PHI_THREADS + threadIdx.x;
     const int s = seg0 + blockIdx.y;
-    if (k >= dm.Ks) return;
-    const int blocks_per_seg = dm.Vp / PHI_SEGMENTS / PHI_ROW_BLOCK;
-    const double *p = partial + (size_t)s * blocks_per_seg * dm.Ks + k;
-    double acc = 0.0;
-    for (int b = 0; b < blocks_per_seg; ++b) acc = __dadd_rn(acc, p[(size_t)b * dm.Ks]);
-    seg[(size_t)s * dm.Ks + k] = acc;
+    if (k < dm.Ks) {
+        const int blocks_per_seg = dm.Vp / PHI_SEGMENTS / PHI_ROW_BLOCK;
+        const double *p = partial + (size_t)s * blocks_per_seg * dm.Ks + k;
+        double acc = 0.0;
+        for (int b = 0; b < blocks_per_seg; ++b) acc = __dadd_rn(acc, p[(size_t)b * dm.Ks]);
+        if (P2P) {
+#pragma unroll
+            for (int q = 0; q < P2P_MAX; ++q)
+                if (q < pt.world) pt.seg[q][(size_t)s * dm.Ks + k] = acc;
+        } else {
+            seg[(size_t)s * dm.Ks + k] = acc;
+        }
+    }
+    if (P2P) p2p_cta_done_signal(pt, P2P_FLAG_SEG, epoch_seg, gridDim.x * gridDim.y);
 }
 
 cudaError_t launch_phi_segment_sums(const Dims &dm, const double *partial, double *seg, int seg0,
@@ -135,35 +200,62 @@ cudaError_t launch_phi_segment_sums(const Dims &dm, const double *partial, doubl
 {
     if (seg1 <= seg0) return cudaSuccess;
     dim3 grid((dm.Ks + PHI_THREADS - 1) / PHI_THREADS, seg1 - seg0);
-    phi_segment_kernel<<<grid, PHI_THREADS, 0, st>>>(dm, partial, seg, seg0);
+    phi_segment_kernel<false><<<grid, PHI_THREADS, 0, st>>>(PeerTable{}, 0u, dm, partial, seg, seg0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_phi_segment_sums_p2p(const PeerTable &pt, uint32_t epoch_seg, const Dims &dm, const double *partial,
+                                        int seg0, int seg1, cudaStream_t st)
+{
+    if (seg1 <= seg0) return cudaErrorInvalidValue;   // every rank owns at least one segment
+    dim3 grid((dm.Ks + PHI_THREADS - 1) / PHI_THREADS, seg1 - seg0);
+    phi_segment_kernel<true><<<grid, PHI_THREADS, 0, st>>>(pt, epoch_seg, dm, partial, nullptr, seg0);
     return cudaGetLastError();
 }
 
 constexpr int NORM_ROWS = 16;
 
+// P2P: waits for every rank's segment sums, and stores the normalised rows of the rank's vocabulary
+// slice into EVERY rank's Phi^T (the all-gather of the sweep as NVLink stores from the producing
+// kernel); the last CTA publishes "Phi rows of rank r are in place".
+template <bool P2P>
 __global__ void __launch_bounds__(PHI_THREADS)
-phi_normalise_kernel(Dims dm, const double *__restrict__ seg, double *__restrict__ topic_sum,
-                     float *__restrict__ phiT, double *__restrict__ mean_sum, int32_t row0, int32_t row1)
+phi_normalise_kernel(PeerTable pt, uint32_t epoch_seg, uint32_t epoch_phi, Dims dm, const double *__restrict__ seg,
+                     double *__restrict__ topic_sum, float *__restrict__ phiT, double *__restrict__ mean_sum,
+                     int32_t row0, int32_t row1)
 {
-    const int k = blockIdx.y * PHI_THREADS + threadIdx.x;
-    if (k >= dm.K) return;
-    double s[PHI_SEGMENTS];
-#pragma unroll
-    for (int i = 0; i < PHI_SEGMENTS; ++i) s[i] = seg[(size_t)i * dm.Ks + k];
-    const double S = __dadd_rn(__dadd_rn(__dadd_rn(s[0], s[1]), __dadd_rn(s[2], s[3])),
-                               __dadd_rn(__dadd_rn(s[4], s[5]), __dadd_rn(s[6], s[7])));
-    if (blockIdx.x == 0 && topic_sum) topic_sum[k] = S;
-    const int32_t wa = row0 + blockIdx.x * NORM_ROWS;
-    for (int32_t w = wa; w < wa + NORM_ROWS && w < row1 && w < dm.V; ++w) {
-        const size_t idx = (size_t)w * dm.Ks + k;
-        float v = phiT[idx];
-        if (S != 0.0) {
-            v = __double2float_rn(__ddiv_rn((double)v, S));
-            if (v <= 0.0f) v = 0x1p-149f;   // ParallelDirichlet.java:63-65 floors at Double.MIN_VALUE
-            phiT[idx] = v;
-        }
-        if (mean_sum) mean_sum[idx] += (double)v;   // LDAGroupedGibbsSampler.java:193-197
+    if (P2P) {
+        if (threadIdx.x == 0) p2p_wait_all(pt, P2P_FLAG_SEG, epoch_seg);
+        __syncthreads();
+        seg = pt.seg[pt.rank];
+        phiT = pt.phiT[pt.rank];
     }
+    const int k = blockIdx.y * PHI_THREADS + threadIdx.x;
+    if (k < dm.K) {
+        double s[PHI_SEGMENTS];
+#pragma unroll
+        for (int i = 0; i < PHI_SEGMENTS; ++i) s[i] = P2P ? __ldcg(seg + (size_t)i * dm.Ks + k) : seg[(size_t)i * dm.Ks + k];
+        const double S = __dadd_rn(__dadd_rn(__dadd_rn(s[0], s[1]), __dadd_rn(s[2], s[3])),
+                                   __dadd_rn(__dadd_rn(s[4], s[5]), __dadd_rn(s[6], s[7])));
+        if (blockIdx.x == 0 && topic_sum) topic_sum[k] = S;
+        const int32_t wa = row0 + blockIdx.x * NORM_ROWS;
+        for (int32_t w = wa; w < wa + NORM_ROWS && w < row1 && w < dm.V; ++w) {
+            const size_t idx = (size_t)w * dm.Ks + k;
+            float v = phiT[idx];
+            if (S != 0.0) {
+                v = __double2float_rn(__ddiv_rn((double)v, S));
+                if (v <= 0.0f) v = 0x1p-149f;   // ParallelDirichlet.java:63-65 floors at Double.MIN_VALUE
+                if (!P2P) phiT[idx] = v;
+            }
+            if (P2P) {
+#pragma unroll
+                for (int q = 0; q < P2P_MAX; ++q)
+                    if (q < pt.world) pt.phiT[q][idx] = v;
+            }
+            if (mean_sum) mean_sum[idx] += (double)v;   // LDAGroupedGibbsSampler.java:193-197
+        }
+    }
+    if (P2P) p2p_cta_done_signal(pt, P2P_FLAG_PHI, epoch_phi, gridDim.x * gridDim.y);
 }
 
 cudaError_t launch_phi_normalise(const Dims &dm, const double *seg, double *topic_sum, float *phiT,
@@ -171,7 +263,19 @@ cudaError_t launch_phi_normalise(const Dims &dm, const double *seg, double *topi
 {
     if (row1 <= row0) return cudaSuccess;
     dim3 grid((row1 - row0 + NORM_ROWS - 1) / NORM_ROWS, (dm.K + PHI_THREADS - 1) / PHI_THREADS);
-    phi_normalise_kernel<<<grid, PHI_THREADS, 0, st>>>(dm, seg, topic_sum, phiT, phi_mean_sum, row0, row1);
+    phi_normalise_kernel<false><<<grid, PHI_THREADS, 0, st>>>(PeerTable{}, 0u, 0u, dm, seg, topic_sum, phiT, phi_mean_sum,
+                                                              row0, row1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_phi_normalise_p2p(const PeerTable &pt, uint32_t epoch_seg, uint32_t epoch_phi, const Dims &dm,
+                                     double *topic_sum, double *phi_mean_sum, int32_t row0, int32_t row1,
+                                     cudaStream_t st)
+{
+    if (row1 <= row0) return cudaErrorInvalidValue;   // every rank owns rows
+    dim3 grid((row1 - row0 + NORM_ROWS - 1) / NORM_ROWS, (dm.K + PHI_THREADS - 1) / PHI_THREADS);
+    phi_normalise_kernel<true><<<grid, PHI_THREADS, 0, st>>>(pt, epoch_seg, epoch_phi, dm, nullptr, topic_sum, nullptr,
+                                                             phi_mean_sum, row0, row1);
     return cudaGetLastError();
 }
 

@@ -451,6 +451,13 @@ class GpuLDASampler:
         self._L.ldagpu_get_last_call_stats(self._h, C.byref(cm), C.byref(ms), C.byref(zl), C.byref(tl))
         return cm.value, ms.value, zl.value, tl.value
 
+    def getExchangeMode(self) -> str:
+        """How the ranks exchange counts and Phi: "single", "nccl" (collectives around the Phi kernels) or
+        "p2p" (the Phi kernels read/write the other ranks' memory over NVLink themselves)."""
+        m = C.c_int32(0)
+        self._L.ldagpu_get_exchange_mode(self._h, C.byref(m))
+        return ("single", "nccl", "p2p")[m.value]
+
     # step-wise access for tests
     def _step(self, name: str):
         self._need()

@@ -47,8 +47,22 @@ def main():
         checks = dict(z=np.array_equal(z, st["z"]), n_wk=np.array_equal(n_wk, st["n_wk"]),
                       n_k=np.array_equal(n_k, st["n_k"]), phi=np.array_equal(phi, st["phiT"]),
                       ll=abs(ll - want_ll) <= 1e-9 * abs(want_ll))
+        # z-only sweep (Phi frozen): stand-alone count exchange, no Phi draw
+        s.sampleZGivenPhi(1)
+        zs = [None] * world
+        dist.all_gather_object(zs, s.get_z_flat())
+        z3 = np.concatenate(zs)
+        nw3, nk3 = O.rebuild_counts(tokens, z3, V, K)
+        checks["zonly_phi_kept"] = np.array_equal(s.getPhi().T.astype(np.float32), st["phiT"])
+        checks["zonly_n_wk"] = np.array_equal(s.getTypeTopicMatrix(), nw3)
+        checks["zonly_n_k"] = np.array_equal(s.getTopicTotals(), nk3)
+        # step-wise API: count rebuild with its own exchange, then a Phi draw on already-merged counts
+        s._step("rebuild_counts")
+        s._step("sample_phi")
+        checks["step_n_wk"] = np.array_equal(s.getTypeTopicMatrix(), nw3)
+        checks["step_phi"] = np.array_equal(s.getPhi().T.astype(np.float32), O.phi_contract(nw3, beta, seed, 3))
         if rank == 0:
-            print(scheme, K, checks, flush=True)
+            print(scheme, K, s.getExchangeMode(), checks, flush=True)
         ok &= all(checks.values())
         s.close()
     t = torch.tensor([1 if ok else 0], device="cuda")
