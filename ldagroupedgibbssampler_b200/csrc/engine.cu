@@ -414,6 +414,10 @@ int run_sweeps(ldagpu_handle h, int32_t n, bool with_phi, int32_t *done)
         cudaEvent_t *ev = h->events.data() + (size_t)s * EV_PER_SWEEP;
         float ms[EV_PER_SWEEP - 1];
         for (int i = 0; i + 1 < EV_PER_SWEEP; ++i) CK(h, cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+        if (getenv("LDAGPU_TRACE"))
+            fprintf(stderr, "[ldagpu rank %d sweep %d] theta %.3f z %.3f totals %.3f exchange %.3f draw+seg %.3f seg-gather %.3f "
+                            "normalise %.3f phi-gather/wait+alias %.3f ms\n", h->rank, h->iteration - ran + s + 1, ms[0], ms[1], ms[2],
+                    ms[3], ms[4], ms[5], ms[6], ms[7]);
         h->t_z += ms[0] + ms[1];
         h->last_zk_ms += ms[1];
         h->t_counts += ms[2];

@@ -22,6 +22,7 @@
 namespace ldagpu {
 
 constexpr int PHI_THREADS = 128;
+constexpr int MAX_GRID_Y = 65535;
 
 // One CTA = 8 words x 128 topics.  Phase 1: every thread runs attempt 0 of its 8 cells in lock step
 // for the ZERO-COUNT cells (shape = beta: the Marsaglia-Tsang constants are shared, as the reference's
@@ -47,8 +48,10 @@ phi_draw_kernel(PeerTable pt, uint32_t epoch_counts, Dims dm, int32_t *n_wk, int
     __shared__ unsigned short s_list[PHI_ROW_BLOCK * PHI_THREADS];
     __shared__ int s_count, s_next;
     const int tid = threadIdx.x;
-    const int k = blockIdx.y * PHI_THREADS + tid;
-    const int32_t wb = row0 + blockIdx.x * PHI_ROW_BLOCK;
+    // topic chunks vary fastest over the grid: the CTAs in flight together cover whole rows, so local and
+    // peer accesses walk Phi^T / n_wk contiguously
+    const int k = blockIdx.x * PHI_THREADS + tid;
+    const int32_t wb = row0 + blockIdx.y * PHI_ROW_BLOCK;
     const bool col_ok = k < dm.Ks;
     if (tid == 0) { s_count = 0; s_next = PHI_THREADS; }
     if (REDUCE) {
@@ -75,7 +78,7 @@ phi_draw_kernel(PeerTable pt, uint32_t epoch_counts, Dims dm, int32_t *n_wk, int
             s_g[r][tid] = 0.0f;
             if (col_ok && w < dm.V) n_wk[(size_t)w * dm.Ks + k] = acc[r];
         }
-        if (blockIdx.x == 0 && col_ok) {
+        if (blockIdx.y == 0 && col_ok) {
             const int32_t *parts = pt.nk_parts[pt.rank];
             int32_t t = 0;
             for (int q = 0; q < pt.world; ++q) t += __ldcg(parts + (size_t)q * dm.Ks + k);
@@ -128,7 +131,7 @@ phi_draw_kernel(PeerTable pt, uint32_t epoch_counts, Dims dm, int32_t *n_wk, int
         const int e = s_list[idx];
         const int r = e / PHI_THREADS, col = e % PHI_THREADS;
         const unsigned long long cell = (unsigned long long)(wb + r) * (unsigned long long)dm.K +
-                                        (unsigned long long)(blockIdx.y * PHI_THREADS + col);
+                                        (unsigned long long)(blockIdx.x * PHI_THREADS + col);
         const double g = c_gamma<double>(__dadd_rn(beta, __int2double_rn(s_n[r][col])), seed_lo, seed_hi, cell,
                                          sweep, STREAM_PHI);
         s_g[r][col] = __double2float_rn(g);
@@ -151,10 +154,13 @@ cudaError_t launch_phi_draw(const Dims &dm, const int32_t *n_wk, double beta, fl
                             double *partial, int32_t row0, int32_t row1, uint32_t seed_lo,
                             uint32_t seed_hi, uint32_t sweep, cudaStream_t st)
 {
-    if (row1 <= row0) return cudaSuccess;
-    dim3 grid((row1 - row0) / PHI_ROW_BLOCK, (dm.Ks + PHI_THREADS - 1) / PHI_THREADS);
-    phi_draw_kernel<false><<<grid, PHI_THREADS, 0, st>>>(PeerTable{}, 0u, dm, const_cast<int32_t *>(n_wk), nullptr, beta,
-                                                         phiT, partial, row0, seed_lo, seed_hi, sweep);
+    // grid.y is limited to 65535: very large vocabularies go in slabs of rows
+    for (int32_t r0 = row0; r0 < row1; r0 += MAX_GRID_Y * PHI_ROW_BLOCK) {
+        const int32_t r1 = r0 + MAX_GRID_Y * PHI_ROW_BLOCK < row1 ? r0 + MAX_GRID_Y * PHI_ROW_BLOCK : row1;
+        dim3 grid((dm.Ks + PHI_THREADS - 1) / PHI_THREADS, (r1 - r0) / PHI_ROW_BLOCK);
+        phi_draw_kernel<false><<<grid, PHI_THREADS, 0, st>>>(PeerTable{}, 0u, dm, const_cast<int32_t *>(n_wk), nullptr,
+                                                             beta, phiT, partial, r0, seed_lo, seed_hi, sweep);
+    }
     return cudaGetLastError();
 }
 
@@ -163,10 +169,12 @@ cudaError_t launch_phi_draw_p2p(const PeerTable &pt, bool reduce_counts, uint32_
                                 int32_t row1, uint32_t seed_lo, uint32_t seed_hi, uint32_t sweep, cudaStream_t st)
 {
     if (!reduce_counts) return launch_phi_draw(dm, n_wk, beta, phiT, partial, row0, row1, seed_lo, seed_hi, sweep, st);
-    if (row1 <= row0) return cudaSuccess;
-    dim3 grid((row1 - row0) / PHI_ROW_BLOCK, (dm.Ks + PHI_THREADS - 1) / PHI_THREADS);
-    phi_draw_kernel<true><<<grid, PHI_THREADS, 0, st>>>(pt, epoch_counts, dm, n_wk, n_k, beta, phiT, partial, row0,
-                                                        seed_lo, seed_hi, sweep);
+    for (int32_t r0 = row0; r0 < row1; r0 += MAX_GRID_Y * PHI_ROW_BLOCK) {
+        const int32_t r1 = r0 + MAX_GRID_Y * PHI_ROW_BLOCK < row1 ? r0 + MAX_GRID_Y * PHI_ROW_BLOCK : row1;
+        dim3 grid((dm.Ks + PHI_THREADS - 1) / PHI_THREADS, (r1 - r0) / PHI_ROW_BLOCK);
+        phi_draw_kernel<true><<<grid, PHI_THREADS, 0, st>>>(pt, epoch_counts, dm, n_wk, n_k, beta, phiT, partial, r0,
+                                                            seed_lo, seed_hi, sweep);
+    }
     return cudaGetLastError();
 }
 
@@ -230,15 +238,15 @@ phi_normalise_kernel(PeerTable pt, uint32_t epoch_seg, uint32_t epoch_phi, Dims 
         seg = pt.seg[pt.rank];
         phiT = pt.phiT[pt.rank];
     }
-    const int k = blockIdx.y * PHI_THREADS + threadIdx.x;
+    const int k = blockIdx.x * PHI_THREADS + threadIdx.x;   // topic chunks fastest (see phi_draw_kernel)
     if (k < dm.K) {
         double s[PHI_SEGMENTS];
 #pragma unroll
         for (int i = 0; i < PHI_SEGMENTS; ++i) s[i] = P2P ? __ldcg(seg + (size_t)i * dm.Ks + k) : seg[(size_t)i * dm.Ks + k];
         const double S = __dadd_rn(__dadd_rn(__dadd_rn(s[0], s[1]), __dadd_rn(s[2], s[3])),
                                    __dadd_rn(__dadd_rn(s[4], s[5]), __dadd_rn(s[6], s[7])));
-        if (blockIdx.x == 0 && topic_sum) topic_sum[k] = S;
-        const int32_t wa = row0 + blockIdx.x * NORM_ROWS;
+        if (blockIdx.y == 0 && topic_sum) topic_sum[k] = S;
+        const int32_t wa = row0 + blockIdx.y * NORM_ROWS;
         for (int32_t w = wa; w < wa + NORM_ROWS && w < row1 && w < dm.V; ++w) {
             const size_t idx = (size_t)w * dm.Ks + k;
             float v = phiT[idx];
@@ -261,10 +269,12 @@ phi_normalise_kernel(PeerTable pt, uint32_t epoch_seg, uint32_t epoch_phi, Dims 
 cudaError_t launch_phi_normalise(const Dims &dm, const double *seg, double *topic_sum, float *phiT,
                                  double *phi_mean_sum, int32_t row0, int32_t row1, cudaStream_t st)
 {
-    if (row1 <= row0) return cudaSuccess;
-    dim3 grid((row1 - row0 + NORM_ROWS - 1) / NORM_ROWS, (dm.K + PHI_THREADS - 1) / PHI_THREADS);
-    phi_normalise_kernel<false><<<grid, PHI_THREADS, 0, st>>>(PeerTable{}, 0u, 0u, dm, seg, topic_sum, phiT, phi_mean_sum,
-                                                              row0, row1);
+    for (int32_t r0 = row0; r0 < row1; r0 += MAX_GRID_Y * NORM_ROWS) {
+        const int32_t r1 = r0 + MAX_GRID_Y * NORM_ROWS < row1 ? r0 + MAX_GRID_Y * NORM_ROWS : row1;
+        dim3 grid((dm.K + PHI_THREADS - 1) / PHI_THREADS, (r1 - r0 + NORM_ROWS - 1) / NORM_ROWS);
+        phi_normalise_kernel<false><<<grid, PHI_THREADS, 0, st>>>(PeerTable{}, 0u, 0u, dm, seg, topic_sum, phiT,
+                                                                  phi_mean_sum, r0, r1);
+    }
     return cudaGetLastError();
 }
 
@@ -273,7 +283,8 @@ cudaError_t launch_phi_normalise_p2p(const PeerTable &pt, uint32_t epoch_seg, ui
                                      cudaStream_t st)
 {
     if (row1 <= row0) return cudaErrorInvalidValue;   // every rank owns rows
-    dim3 grid((row1 - row0 + NORM_ROWS - 1) / NORM_ROWS, (dm.K + PHI_THREADS - 1) / PHI_THREADS);
+    if ((row1 - row0 + NORM_ROWS - 1) / NORM_ROWS > MAX_GRID_Y) return cudaErrorInvalidConfiguration;   // > 1M rows per rank
+    dim3 grid((dm.K + PHI_THREADS - 1) / PHI_THREADS, (row1 - row0 + NORM_ROWS - 1) / NORM_ROWS);
     phi_normalise_kernel<true><<<grid, PHI_THREADS, 0, st>>>(pt, epoch_seg, epoch_phi, dm, nullptr, topic_sum, nullptr,
                                                              phi_mean_sum, row0, row1);
     return cudaGetLastError();
