@@ -11,8 +11,8 @@
 // Phi^T row is read as coalesced float4.  Rows are fetched by the TMA engine (cp.async.bulk,
 // 1-D) into a per-warp shared-memory ring, a few rows ahead of the consumer.  A run of equal
 // word types shares one row fetch (and, for GGS, one prefix scan).  The categorical draw is a
-// fixed three-level fp32 prefix tree (lane-local prefix, Kogge-Stone warp scan, sequential tile
-// bases) so the CPU oracle can reproduce the sampled topic bit for bit; uniforms are
+// fixed three-level fp32 prefix tree (lane-local fma prefix, distributed-butterfly tile totals,
+// Kogge-Stone scan inside the chosen tile) so the CPU oracle can reproduce the sampled topic bit for bit; uniforms are
 // Philox4x32-10 keyed by the global token index.
 #include "common.cuh"
 #include "contract_math.cuh"
@@ -24,14 +24,14 @@ constexpr unsigned FULL = 0xffffffffu;
 // kernel is bound by shuffle/shared-pipe latency, not by row fetches (83 % of them hit L2), so
 // resident warps matter more than prefetch depth: 1 ring slot and 4 CTAs/SM (32 warps, 64
 // registers, 72 B of spills at K=1000) beat 3 slots and 2 CTAs/SM by 20 %.
-#ifndef Z_STAGES_DEF
-#define Z_STAGES_DEF 1
-#endif
 #ifndef Z_MINB_DEF
 #define Z_MINB_DEF 4
 #endif
-constexpr int Z_WARPS = 8;               // warps per CTA
-constexpr int Z_STAGES = Z_STAGES_DEF;   // Phi^T row slots per warp (the row also lives in registers)
+// warps per CTA.  GGS at 1024 topics keeps theta (32 registers) and the prefixes (32) live: 7 warps x 4 CTAs
+// leave 72 registers per thread instead of 64 and halve the spill reloads, which ride on the same
+// shared-memory data pipe (128 B per clock per SM) that bounds this kernel (profiles/README.md)
+template <int NT, bool PCGS> __host__ __device__ constexpr int z_warps() { return (NT == 8 && !PCGS) ? 7 : 8; }
+constexpr int Z_STAGES = 1;               // one Phi^T row slot per warp (the row also lives in registers)
 
 template <int NT> struct RowScan {
     float p[NT][4];   // lane-local inclusive prefix of the 4 owned scores, per tile (p[j][3] = lane total)
@@ -50,10 +50,11 @@ __device__ __forceinline__ void scan_scores(const float4 (&a)[NT], const float4 
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         if (j < NT) {
+            // lane-local prefix as one product and three fused multiply-adds (contract 4.2)
             float p0 = __fmul_rn(a[j < NT ? j : 0].x, ph[j < NT ? j : 0].x);
-            float p1 = __fadd_rn(p0, __fmul_rn(a[j < NT ? j : 0].y, ph[j < NT ? j : 0].y));
-            float p2 = __fadd_rn(p1, __fmul_rn(a[j < NT ? j : 0].z, ph[j < NT ? j : 0].z));
-            float p3 = __fadd_rn(p2, __fmul_rn(a[j < NT ? j : 0].w, ph[j < NT ? j : 0].w));
+            float p1 = __fmaf_rn(a[j < NT ? j : 0].y, ph[j < NT ? j : 0].y, p0);
+            float p2 = __fmaf_rn(a[j < NT ? j : 0].z, ph[j < NT ? j : 0].z, p1);
+            float p3 = __fmaf_rn(a[j < NT ? j : 0].w, ph[j < NT ? j : 0].w, p2);
             rs.p[j < NT ? j : 0][0] = p0; rs.p[j < NT ? j : 0][1] = p1;
             rs.p[j < NT ? j : 0][2] = p2; rs.p[j < NT ? j : 0][3] = p3;
             t[j] = p3;
@@ -141,16 +142,17 @@ template <int NT, bool PCGS> __host__ __device__ constexpr size_t z_warp_smem()
 }
 template <int NT, bool PCGS> __host__ __device__ constexpr size_t z_cta_smem()
 {
-    return Z_WARPS * z_warp_smem<NT, PCGS>() + (PCGS ? (size_t)NT * TILE * 4 : 0) +
-           (size_t)Z_WARPS * Z_STAGES * 8;
+    return z_warps<NT, PCGS>() * z_warp_smem<NT, PCGS>() + (PCGS ? (size_t)NT * TILE * 4 : 0) +
+           (size_t)z_warps<NT, PCGS>() * Z_STAGES * 8;
 }
 
 template <int NT, bool PCGS>
-__global__ void __launch_bounds__(Z_WARPS * 32, (PCGS && NT == 8) ? 2 : Z_MINB_DEF) z_kernel(ZArgs a)
+__global__ void __launch_bounds__(z_warps<NT, PCGS>() * 32, (PCGS && NT == 8) ? 2 : Z_MINB_DEF) z_kernel(ZArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int ROWF = NT * TILE;
+    constexpr int Z_WARPS = z_warps<NT, PCGS>();
     unsigned char *wbase = smem_raw + (size_t)warp * z_warp_smem<NT, PCGS>();
     float *ring = reinterpret_cast<float *>(wbase);
     int *cnt = reinterpret_cast<int *>(wbase + (size_t)Z_STAGES * ROWF * 4);       // PCGS only
@@ -177,7 +179,9 @@ __global__ void __launch_bounds__(Z_WARPS * 32, (PCGS && NT == 8) ? 2 : Z_MINB_D
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (PCGS) __syncthreads(); else __syncwarp();
 
-    uint32_t fill = 0, cons = 0;   // rows issued / consumed so far by this warp (warp-uniform)
+    uint32_t phase = 0;            // parity of the slot's mbarrier (one completed fetch flips it)
+    float *const slot = ring;
+    uint64_t *const bar = bars;
 
     for (;;) {
         unsigned long long item = 0;
@@ -236,69 +240,60 @@ __global__ void __launch_bounds__(Z_WARPS * 32, (PCGS && NT == 8) ? 2 : Z_MINB_D
                 U = uniform23(r.x);
             }
             int znew = 0;
-            unsigned pending = heads;   // run heads whose row has not been requested yet
-
-            // producer: keep up to Z_STAGES row fetches in flight
-            auto produce = [&]() {
-                while (pending && fill - cons < (uint32_t)Z_STAGES) {
-                    int b = __ffs(pending) - 1;
-                    pending &= pending - 1;
-                    int wrow = __shfl_sync(FULL, w, b);
-                    if (lane == 0) {
-                        uint32_t slot = fill % Z_STAGES;
-                        mbar_expect_tx(&bars[slot], row_bytes);
-                        bulk_g2s(ring + (size_t)slot * ROWF, a.phiT + (size_t)wrow * Ks, row_bytes, &bars[slot]);
-                    }
-                    ++fill;
+            // One row slot per warp: the row of a run is copied to registers as soon as it lands, and the
+            // slot is refilled with the next run's row while the warp computes (lane 0 drives the TMA).
+            auto request = [&](int head_lane) {
+                const int wrow = __shfl_sync(FULL, w, head_lane);
+                if (lane == 0) {
+                    mbar_expect_tx(bar, row_bytes);
+                    bulk_g2s(slot, a.phiT + (size_t)wrow * Ks, row_bytes, bar);
                 }
             };
-            produce();
-
-            unsigned rem = heads;
-            while (rem) {
-                const int b = __ffs(rem) - 1;
+            unsigned rem = heads;          // lane 0 of a non-empty block is always a head
+            int b = 0;
+            request(0);
+            for (;;) {
                 rem &= rem - 1;
                 const int e = rem ? __ffs(rem) - 1 : nvalid;   // run = tokens [b, e) of this block
-                const uint32_t slot = cons % Z_STAGES;
-                mbar_wait(&bars[slot], (cons / Z_STAGES) & 1u);
+                mbar_wait(bar, phase);
+                phase ^= 1u;
                 float4 ph[NT];
 #pragma unroll
-                for (int j = 0; j < NT; ++j)
-                    ph[j] = reinterpret_cast<const float4 *>(ring + (size_t)slot * ROWF)[j * 32 + lane];
+                for (int j = 0; j < NT; ++j) ph[j] = reinterpret_cast<const float4 *>(slot)[j * 32 + lane];
                 __syncwarp();
-                ++cons;
-                produce();   // the slot is free again: request the next row while we compute
+                if (rem) request(e);
 
                 RowScan<NT> rs;
                 if (!PCGS) scan_scores<NT>(th, ph, rs, lane);
                 for (int tt = b; tt < e; ++tt) {
                     if (PCGS) {
-                        // remove the token from the document counts (UncollapsedParallelLDA.java:1494)
-                        int old = __shfl_sync(FULL, zold, tt);
-                        if (lane == 0) {
-                            int c = cnt[old] - 1;
-                            cnt[old] = c;
-                            av[old] = __fadd_rn(__int2float_rn(c), alpha_s[old]);
-                        }
+                        // remove the token from the document counts (UncollapsedParallelLDA.java:1494);
+                        // every lane computes the new entry (broadcast reads), lane 0 stores it
+                        const int old = __shfl_sync(FULL, zold, tt);
+                        const int c = cnt[old] - 1;
+                        const float v = __fadd_rn(__int2float_rn(c), alpha_s[old]);
+                        __syncwarp();
+                        if (lane == 0) { cnt[old] = c; av[old] = v; }
                         __syncwarp();
                         float4 aa[NT];
 #pragma unroll
                         for (int j = 0; j < NT; ++j) aa[j] = reinterpret_cast<const float4 *>(av)[j * 32 + lane];
                         scan_scores<NT>(aa, ph, rs, lane);
                     }
-                    float Ut = __shfl_sync(FULL, U, tt);
-                    int k = draw_topic<NT>(rs, Ut, lane, K);
+                    const float Ut = __shfl_sync(FULL, U, tt);
+                    const int k = draw_topic<NT>(rs, Ut, lane, K);
                     if (lane == tt) znew = k;
                     if (PCGS) {
                         // add it back under its new topic (UncollapsedParallelLDA.java:1535)
-                        if (lane == 0) {
-                            int c = cnt[k] + 1;
-                            cnt[k] = c;
-                            av[k] = __fadd_rn(__int2float_rn(c), alpha_s[k]);
-                        }
+                        const int c = cnt[k] + 1;
+                        const float v = __fadd_rn(__int2float_rn(c), alpha_s[k]);
+                        __syncwarp();
+                        if (lane == 0) { cnt[k] = c; av[k] = v; }
                         __syncwarp();
                     }
                 }
+                if (!rem) break;
+                b = e;
             }
             if (valid) {
                 a.z[t] = znew;
@@ -320,6 +315,7 @@ template <int NT, bool PCGS>
 static cudaError_t launch_z_t(const ZArgs &a, int sm_count, cudaStream_t st)
 {
     constexpr size_t smem = z_cta_smem<NT, PCGS>();
+    constexpr int Z_WARPS = z_warps<NT, PCGS>();
     static bool configured = false;
     static int ctas_per_sm = 1;
     if (!configured) {
@@ -360,7 +356,8 @@ cudaError_t launch_z_pcgs(const ZArgs &a, int sm_count, cudaStream_t st) { retur
 //   phase 1  branch-free lock step over the lane's 4*NT cells: attempt 0 of every ZERO-COUNT cell
 //            (shape = alpha_k, the vast majority; Marsaglia-Tsang constants from a per-CTA table,
 //            cf. the reference's MarsagliaSparseDirichlet.java:9-29) is settled when the squeeze
-//            accepts it (~92 %); all other cells go to a per-warp list in shared memory
+//            accepts it (~92 %); all other cells are appended to a per-warp list in shared memory
+//            in the same step (ballot + popc)
 //   phase 2  the list is drained by all 32 lanes with a flattened attempt loop: a lane whose cell
 //            is accepted takes the next list entry, so rejections do not idle the warp
 //   phase 3  normalising sum in the contract's order (lane-sequential, then xor butterfly), divide,
@@ -452,8 +449,8 @@ __global__ void __launch_bounds__(TH_WARPS * 32) theta_kernel(ThetaArgs a)
             __syncwarp();
         };
 
-        // ---- phase 1 (pending cells are remembered in a per-lane bit mask: NT <= 8 => 32 cells)
-        unsigned pend = 0;
+        // ---- phase 1; the cells it leaves open are appended to the pending list as they are found
+        //      (ballot + popc, all lanes) and the list is drained whenever another 32 might not fit
         for (int q = 0; q < NT * 4; ++q) {
             const int k = (q >> 2) * TILE + lane * 4 + (q & 3);
             const bool valid = k < K;
@@ -467,31 +464,13 @@ __global__ void __launch_bounds__(TH_WARPS * 32) theta_kernel(ThetaArgs a)
                 done = gamma_attempt_squeeze<float>(ii_ > 0.0f, d0[k], c0[k], ii_, w, gv);
                 if (done) cg[k] = __float_as_int(gv);
             }
-            pend |= (done ? 0u : 1u) << q;
+            const unsigned open_mask = __ballot_sync(FULL, !done);
+            if (!done) plist[npend + __popc(open_mask & lt_mask)] = (unsigned short)k;
+            npend += __popc(open_mask);
+            if (npend > TH_PLIST - 32) drain();
         }
-        // ---- phase 2: compact the pending cells of all lanes into the list, TH_PLIST at a time
-        {
-            int mine = __popc(pend), incl = mine;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                int y = __shfl_up_sync(FULL, incl, off);
-                if (lane >= off) incl += y;
-            }
-            const int total = __shfl_sync(FULL, incl, 31);
-            for (int lo = 0; lo < total; lo += TH_PLIST) {
-                int pos = incl - mine;
-                unsigned bits = pend;
-                while (bits) {
-                    const int q = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    if (pos >= lo && pos < lo + TH_PLIST)
-                        plist[pos - lo] = (unsigned short)((q >> 2) * TILE + lane * 4 + (q & 3));
-                    ++pos;
-                }
-                npend = min(total - lo, TH_PLIST);
-                drain();
-            }
-        }
+        // ---- phase 2
+        if (npend > 0) drain();
         __syncwarp();
         // ---- phase 3: sum in contract order, normalise, store
         const float4 *g4 = reinterpret_cast<const float4 *>(cg);
@@ -504,12 +483,15 @@ __global__ void __launch_bounds__(TH_WARPS * 32) theta_kernel(ThetaArgs a)
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, off));
         const float sum = acc;
+        // contract 4.3: theta = g * (1 / sum) -- one division per document; the products handle the
+        // many denormal g (alpha << 1) at full speed, where a division would take its slow path
+        const float inv = sum != 0.0f ? __fdiv_rn(1.0f, sum) : 0.0f;
         for (int j = 0; j < NT; ++j) {
             int k0 = j * TILE + lane * 4;
             float4 v = g4[j * 32 + lane];
             if (sum != 0.0f) {
-                v.x = __fdiv_rn(v.x, sum); v.y = __fdiv_rn(v.y, sum);
-                v.z = __fdiv_rn(v.z, sum); v.w = __fdiv_rn(v.w, sum);
+                v.x = __fmul_rn(v.x, inv); v.y = __fmul_rn(v.y, inv);
+                v.z = __fmul_rn(v.z, inv); v.w = __fmul_rn(v.w, inv);
                 if (v.x <= 0.0f) v.x = 0x1p-149f;
                 if (v.y <= 0.0f) v.y = 0x1p-149f;
                 if (v.z <= 0.0f) v.z = 0x1p-149f;

@@ -158,9 +158,9 @@ __global__ void __launch_bounds__(256) z_kernel_big(ZArgs a)
                                     const float4 v = reinterpret_cast<const float4 *>(vec)[j * 32 + lane];
                                     const float4 ph = reinterpret_cast<const float4 *>(row)[j * 32 + lane];
                                     p3 = __fmul_rn(v.x, ph.x);
-                                    p3 = __fadd_rn(p3, __fmul_rn(v.y, ph.y));
-                                    p3 = __fadd_rn(p3, __fmul_rn(v.z, ph.z));
-                                    p3 = __fadd_rn(p3, __fmul_rn(v.w, ph.w));
+                                    p3 = __fmaf_rn(v.y, ph.y, p3);
+                                    p3 = __fmaf_rn(v.z, ph.z, p3);
+                                    p3 = __fmaf_rn(v.w, ph.w, p3);
                                 }
                                 tl[tau] = p3;
                             }
@@ -190,9 +190,9 @@ __global__ void __launch_bounds__(256) z_kernel_big(ZArgs a)
                     const float4 v = reinterpret_cast<const float4 *>(vec)[js * 32 + lane];
                     const float4 ph = reinterpret_cast<const float4 *>(row)[js * 32 + lane];
                     const float q0 = __fmul_rn(v.x, ph.x);
-                    const float q1 = __fadd_rn(q0, __fmul_rn(v.y, ph.y));
-                    const float q2 = __fadd_rn(q1, __fmul_rn(v.z, ph.z));
-                    float inc = __fadd_rn(q2, __fmul_rn(v.w, ph.w));
+                    const float q1 = __fmaf_rn(v.y, ph.y, q0);
+                    const float q2 = __fmaf_rn(v.z, ph.z, q1);
+                    float inc = __fmaf_rn(v.w, ph.w, q2);
 #pragma unroll
                     for (int off = 1; off < 32; off <<= 1) {
                         float y = __shfl_up_sync(FULL, inc, off);
@@ -298,6 +298,7 @@ __global__ void __launch_bounds__(256) theta_kernel_big(ThetaArgs a)
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(FULL, acc, off));
         const float sum = acc;
+        const float inv = sum != 0.0f ? __fdiv_rn(1.0f, sum) : 0.0f;   // contract 4.3: theta = g * (1 / sum)
         for (int j = 0; j < NT; ++j) {
             const int k0 = j * TILE + lane * 4;
             float4 v = reinterpret_cast<const float4 *>(cg)[j * 32 + lane];
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(256) theta_kernel_big(ThetaArgs a)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 if (sum != 0.0f) {
-                    c[i] = __fdiv_rn(c[i], sum);
+                    c[i] = __fmul_rn(c[i], inv);
                     if (c[i] <= 0.0f) c[i] = 0x1p-149f;
                 }
                 if (k0 + i >= K) c[i] = 0.0f;

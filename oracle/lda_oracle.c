@@ -281,7 +281,7 @@ void oracle_doc_topic_counts(int64_t D, const int64_t *doc_off, const int32_t *z
  * (topics/LDAGroupedGibbsSampler.java:96-113, topics/UncollapsedParallelLDA.java:1507-1526)
  * as "first k with cumsum_k >= U*sum" over a fixed fp32 prefix tree:
  *   tile = 128 topics, lane l of 32 owns 4 consecutive topics of the tile; lane-local sequential
- *     prefix p0..p3, lane total t = p3;
+ *     prefix p0 = s0, p_i = fma(a_i, phi_i, p_{i-1}), lane total t = p3;
  *   tile totals, 8 tiles at a time, by a distributed butterfly over the 32 lanes: xor 16 (lanes
  *     with bit 4 clear keep tiles 0-3, the others tiles 4-7), xor 8 (2 tiles kept), xor 4 (1 tile
  *     kept: lane l now works for tile (l>>2)&7), xor 2, xor 1;
@@ -303,8 +303,9 @@ static int32_t draw_topic_contract(const float *a, const float *phirow, int32_t 
             float run = 0.0f;
             for (int i = 0; i < 4; ++i) {
                 int k = 128 * j + 4 * l + i;
-                float s = (k < K) ? a[k] * phirow[k] : 0.0f;
-                run = (i == 0) ? s : run + s;
+                /* one product, then three fused multiply-adds (padding topics add +0) */
+                if (i == 0) run = (k < K) ? a[k] * phirow[k] : 0.0f;
+                else if (k < K) run = fmaf(a[k], phirow[k], run);
                 p[(j * 32 + l) * 4 + i] = run;
             }
         }
@@ -439,11 +440,13 @@ void oracle_theta_contract(int64_t D, const int64_t *doc_off, const int32_t *z, 
                 memcpy(acc, t, sizeof acc);
             }
             float sum = acc[0];
-            if (sum != 0.0f)
+            if (sum != 0.0f) {
+                float inv = 1.0f / sum;   /* one division per document, then K products */
                 for (int k = 0; k < K; ++k) {
-                    float v = th[k] / sum;
+                    float v = th[k] * inv;
                     th[k] = (v <= 0.0f) ? F32_TRUE_MIN : v;
                 }
+            }
         }
         free(cnt);
     }
