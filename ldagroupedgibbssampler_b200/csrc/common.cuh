@@ -7,7 +7,8 @@ namespace ldagpu {
 
 constexpr int TILE = 128;            // topics per warp tile: lane l owns topics 4l..4l+3 of the tile
 constexpr int MAX_REG_TILES = 8;     // K <= 1024 keeps a whole Phi^T row in registers
-constexpr int GGS_CHUNK = 256;       // tokens per GGS work item (documents are split freely)
+constexpr int GGS_CHUNK_MAX = 256;   // most tokens per GGS work item (documents are split freely; the engine
+                                     // picks a multiple of 32 so that every resident warp gets several items)
 constexpr int PHI_ROW_BLOCK = 8;     // words per sequential partial sum of the Phi normaliser
 constexpr int PHI_SEGMENTS = 8;      // vocabulary segments (= max ranks) of the Phi normaliser tree
 
@@ -36,6 +37,7 @@ struct ZArgs {
     const int32_t *item_doc;  // GGS: [n_items] document of each chunk; PCGS: [D] LPT order
     const int64_t *item_begin;// GGS: [n_items] first token of each chunk
     int64_t n_items;
+    int32_t chunk;            // GGS: tokens per work item
     unsigned long long *work_counter;
     int32_t *n_wk_out;        // when set (zeroed by the caller), the z-step also adds the new (w, z) counts
     uint32_t seed_lo, seed_hi, sweep;
@@ -124,9 +126,10 @@ cudaError_t launch_phi_segment_sums(const Dims &dm, const double *partial, doubl
 cudaError_t launch_phi_normalise(const Dims &dm, const double *seg, double *topic_sum, float *phiT,
                                  double *phi_mean_sum, int32_t row0, int32_t row1, cudaStream_t st);
 // log-likelihood pieces: per-block partial sums (ll_type: pairs {sum, nnz})
+cudaError_t launch_lgs_table(int K, const double *alpha, double *out /*[K] lgS(alpha_k)*/, cudaStream_t st);
 cudaError_t launch_ll_doc(const Dims &dm, const int64_t *doc_off, const int32_t *z,
-                          const double *alpha, double alpha_sum, double *partials, int n_partials,
-                          int sm_count, cudaStream_t st);
+                          const double *alpha, const double *lgs_alpha, double alpha_sum, double *partials,
+                          int n_partials, int sm_count, cudaStream_t st);
 cudaError_t launch_ll_type(const Dims &dm, const int32_t *n_wk, double beta, int32_t row0,
                            int32_t row1, double *partials, int n_partials, cudaStream_t st);
 // log-posterior pieces (UncollapsedParallelLDA.java:1573-1634)

@@ -136,10 +136,11 @@ struct ldagpu_handle_s {
     int32_t n_active_types = 0;
     DevBuf<double> alias_bs;
     int max_doc_len = 0;
-    DevBuf<double> alpha_d, partial, seg, topic_sum, phi_mean, red, red_out, scratch_f64;
+    DevBuf<double> alpha_d, lgs_alpha, partial, seg, topic_sum, phi_mean, red, red_out, scratch_f64;
     DevBuf<unsigned long long> counter;
     DevBuf<int> bad;
     int64_t n_items = 0;
+    int32_t ggs_chunk = GGS_CHUNK_MAX;
     std::vector<int64_t> h_doc_off;
 
     int32_t mean_burn_in = 0, mean_thin = 1, n_sampled_phi = 0;
@@ -234,7 +235,7 @@ int step_z(ldagpu_handle h, bool fused = false)
     ZArgs a{};
     a.dm = h->dm; a.doc_off = h->doc_off.p; a.tokens = h->tokens.p; a.z = h->z.p; a.phiT = h->phiT.p;
     a.theta = h->theta.p; a.alpha = h->alpha_f.p; a.item_doc = h->item_doc.p; a.item_begin = h->item_begin.p;
-    a.n_items = h->n_items; a.work_counter = h->counter.p;
+    a.n_items = h->n_items; a.chunk = h->ggs_chunk; a.work_counter = h->counter.p;
     a.n_wk_out = fused ? h->n_wk.p : nullptr;
     a.seed_lo = (uint32_t)h->seed; a.seed_hi = (uint32_t)(h->seed >> 32); a.sweep = (uint32_t)h->iteration;
     if (h->scheme == LDAGPU_SCHEME_GGS) {
@@ -442,9 +443,15 @@ int build_items(ldagpu_handle h)
     std::vector<int32_t> item_doc;
     std::vector<int64_t> item_begin;
     if (h->scheme == LDAGPU_SCHEME_GGS) {
-        // documents split freely into chunks: tokens are independent given theta (GGS:97-101)
+        // documents split freely into chunks: tokens are independent given theta (GGS:97-101).  Few long
+        // documents (NIPS shape: 1 500 documents of ~1 300 tokens) would leave most resident warps with one
+        // item and some with two; smaller chunks give every warp of the persistent grid ~8 items.
+        const int64_t resident_warps = (int64_t)h->sm_count * 40;
+        int64_t chunk = (h->dm.N / (8 * resident_warps) + 31) / 32 * 32;
+        chunk = std::min<int64_t>(std::max<int64_t>(chunk, 32), GGS_CHUNK_MAX);
+        h->ggs_chunk = (int32_t)chunk;
         for (int64_t d = 0; d < D; ++d)
-            for (int64_t t = off[d]; t < off[d + 1]; t += GGS_CHUNK) {
+            for (int64_t t = off[d]; t < off[d + 1]; t += chunk) {
                 item_doc.push_back((int32_t)d);
                 item_begin.push_back(t);
             }
@@ -658,6 +665,7 @@ int ldagpu_create(int32_t K, int32_t V, int64_t D, const int64_t *doc_offsets, c
         CK(h, h->n_k.alloc((size_t)dm.Ks));
         CK(h, h->alpha_f.alloc((size_t)dm.Ks));
         CK(h, h->alpha_d.alloc((size_t)dm.Ks));
+        CK(h, h->lgs_alpha.alloc((size_t)dm.Ks));
         CK(h, h->partial.alloc((size_t)(dm.Vp / PHI_ROW_BLOCK) * dm.Ks));
         CK(h, h->seg.alloc((size_t)PHI_SEGMENTS * dm.Ks));
         CK(h, h->topic_sum.alloc((size_t)dm.Ks));
@@ -704,6 +712,7 @@ int ldagpu_create(int32_t K, int32_t V, int64_t D, const int64_t *doc_offsets, c
         for (int k = 0; k < K; ++k) { af[k] = (float)alpha[k]; ad[k] = alpha[k]; }
         CK(h, cudaMemcpy(h->alpha_f.p, af.data(), sizeof(float) * af.size(), cudaMemcpyHostToDevice));
         CK(h, cudaMemcpy(h->alpha_d.p, ad.data(), sizeof(double) * ad.size(), cudaMemcpyHostToDevice));
+        CK(h, launch_lgs_table(K, h->alpha_d.p, h->lgs_alpha.p, h->stream));
         // type ids must be inside the alphabet (UPL:360 numTypes = alphabet.size())
         CK(h, launch_validate(dm, h->tokens.p, nullptr, h->bad.p, h->stream));
         int bad = 0;
@@ -731,7 +740,7 @@ int ldagpu_destroy(ldagpu_handle h)
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
     h->doc_off.release(); h->item_begin.release(); h->tokens.release(); h->z.release(); h->n_wk.release();
     h->n_k.release(); h->item_doc.release(); h->scratch_i32.release(); h->phiT.release(); h->theta.release();
-    h->alpha_f.release(); h->alpha_d.release(); h->partial.release(); h->seg.release(); h->topic_sum.release();
+    h->alpha_f.release(); h->alpha_d.release(); h->lgs_alpha.release(); h->partial.release(); h->seg.release(); h->topic_sum.release();
     h->phi_mean.release(); h->red.release(); h->red_out.release(); h->scratch_f64.release();
     h->counter.release(); h->bad.release();
     h->alias_ps.release(); h->type_norm.release(); h->alias_al.release(); h->alias_stack.release(); h->alias_bs.release();
@@ -989,7 +998,8 @@ int ldagpu_set_theta(ldagpu_handle h, const double *theta)
 int ldagpu_log_likelihood(ldagpu_handle h, double *ll)
 {
     NEED(h);
-    CK(h, launch_ll_doc(h->dm, h->doc_off.p, h->z.p, h->alpha_d.p, h->alpha_sum, h->red.p, N_PARTIALS, h->sm_count, h->stream));
+    CK(h, launch_ll_doc(h->dm, h->doc_off.p, h->z.p, h->alpha_d.p, h->lgs_alpha.p, h->alpha_sum, h->red.p, N_PARTIALS, h->sm_count,
+                         h->stream));
     CK(h, launch_sum_partials(h->red.p, N_PARTIALS, 1, h->red_out.p, h->stream));
     CK(h, launch_ll_type(h->dm, h->n_wk.p, h->beta, h->row0, h->row1, h->red.p, N_PARTIALS, h->stream));
     CK(h, launch_sum_partials(h->red.p, N_PARTIALS, 2, h->red_out.p + 1, h->stream));

@@ -15,60 +15,36 @@ constexpr unsigned FULL = 0xffffffffu;
 
 // ---------------------------------------------------------------------------------------
 // K3: n_wk[w][k] = #{i : w_i = w, z_i = k},  n_k = column sums.  Integer, exact.
-// int4 loads of (w, z); equal neighbours merged in the thread, then equal keys merged across
-// the warp (match.any + redux) so one atomic goes out per distinct (w, k) per warp step.
+// int4 loads of (w, z); equal neighbours are merged inside the thread (documents are bags of words:
+// equal types are adjacent), one fire-and-forget reduction per distinct cell of the thread's four
+// tokens.  Merging equal cells across the warp as well (match.any + redux) was measured slower on
+// B200 (2.7 ms against 2.0 ms on the PubMed-shaped shard, profiles/README.md): the cells of 32 lanes
+// rarely coincide and the scatter over a 578 MB matrix is bound by L2/DRAM sector traffic, not by the
+// number of reductions.
 // ---------------------------------------------------------------------------------------
 constexpr int CNT_THREADS = 256;
 
-#ifndef CNT_AGG_DEF
-#define CNT_AGG_DEF 1
-#endif
-// One atomic per distinct (w, k) cell per warp step: lanes holding the same 32-bit cell index are
-// found with match.any, their counts summed with redux, and the lowest lane issues the atomic.
-__device__ __forceinline__ void warp_aggregated_add(int32_t *n_wk, unsigned key, int c, int lane)
-{
-    unsigned m = __match_any_sync(FULL, key);
-    int total = __reduce_add_sync(m, c);
-    if (total > 0 && lane == __ffs(m) - 1) atomicAdd(&n_wk[key], total);
-}
-
-template <bool AGG>
 __global__ void __launch_bounds__(CNT_THREADS)
 counts_kernel(Dims dm, const int32_t *__restrict__ tokens, const int32_t *__restrict__ z,
               int32_t *__restrict__ n_wk)
 {
-    const int lane = threadIdx.x & 31;
     const int64_t n4 = dm.N / 4;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    // all lanes of a warp iterate together (match.any needs the whole warp)
-    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane;
-    for (int64_t base = first; base < n4; base += stride) {
-        const int64_t i = base + lane;
-        const bool ok = i < n4;
-        int4 w4 = ok ? __ldg(reinterpret_cast<const int4 *>(tokens) + i) : make_int4(0, 0, 0, 0);
-        int4 z4 = ok ? __ldg(reinterpret_cast<const int4 *>(z) + i) : make_int4(0, 0, 0, 0);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int4 w4 = __ldg(reinterpret_cast<const int4 *>(tokens) + i);
+        const int4 z4 = __ldg(reinterpret_cast<const int4 *>(z) + i);
         size_t key[4];
-        int c[4];
+        int c[4] = {1, 1, 1, 1};
         const int ww[4] = {w4.x, w4.y, w4.z, w4.w};
         const int zz[4] = {z4.x, z4.y, z4.z, z4.w};
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            key[s] = (size_t)ww[s] * (size_t)dm.Ks + (size_t)zz[s];
-            c[s] = ok ? 1 : 0;
-        }
-        // merge equal neighbours inside the thread (documents are bags of words: equal types adjacent)
+        for (int s = 0; s < 4; ++s) key[s] = (size_t)ww[s] * (size_t)dm.Ks + (size_t)zz[s];
 #pragma unroll
         for (int s = 3; s > 0; --s)
             if (key[s] == key[s - 1]) { c[s - 1] += c[s]; c[s] = 0; }
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            if (AGG) {
-                // lanes with nothing to add use a key no cell has (cells < 2^32 - 32 is checked by the launcher)
-                warp_aggregated_add(n_wk, c[s] > 0 ? (unsigned)key[s] : 0xffffffe0u + (unsigned)lane, c[s], lane);
-            } else if (c[s] > 0) {
-                atomicAdd(&n_wk[key[s]], c[s]);
-            }
-        }
+        for (int s = 0; s < 4; ++s)
+            if (c[s] > 0) atomicAdd(&n_wk[key[s]], c[s]);
     }
     // scalar tail (N % 4 tokens), done by block 0
     if (blockIdx.x == 0)
@@ -86,7 +62,7 @@ topic_totals_kernel(Dims dm, const int32_t *__restrict__ n_wk, int32_t *__restri
     int acc = 0;
     const int rows = (dm.V + gridDim.y - 1) / gridDim.y;
     const int w0 = blockIdx.y * rows, w1 = min(w0 + rows, dm.V);
-#pragma unroll 4
+#pragma unroll 8
     for (int w = w0; w < w1; ++w) acc += n_wk[(size_t)w * dm.Ks + k];
     if (acc) atomicAdd(&n_k[k], acc);
 }
@@ -95,7 +71,7 @@ cudaError_t launch_topic_totals(const Dims &dm, const int32_t *n_wk, int32_t *n_
 {
     cudaError_t e = cudaMemsetAsync(n_k, 0, sizeof(int32_t) * (size_t)dm.Ks, st);
     if (e != cudaSuccess) return e;
-    int gy = (dm.V + 255) / 256;
+    int gy = (dm.V + 63) / 64;   // ~64 rows per CTA, eight loads in flight per thread
     if (gy > 1024) gy = 1024;
     if (gy < 1) gy = 1;
     dim3 grid((dm.K + 127) / 128, gy);
@@ -113,9 +89,7 @@ cudaError_t launch_counts(const Dims &dm, const int32_t *tokens, const int32_t *
         int64_t grid = (int64_t)sm_count * 8;
         if (need < grid) grid = need;
         if (grid < 1) grid = 1;
-        const bool agg = CNT_AGG_DEF && (size_t)dm.Vp * (size_t)dm.Ks < 0xffffffe0ull;
-        if (agg) counts_kernel<true><<<(unsigned)grid, CNT_THREADS, 0, st>>>(dm, tokens, z, n_wk);
-        else counts_kernel<false><<<(unsigned)grid, CNT_THREADS, 0, st>>>(dm, tokens, z, n_wk);
+        counts_kernel<<<(unsigned)grid, CNT_THREADS, 0, st>>>(dm, tokens, z, n_wk);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
@@ -196,10 +170,28 @@ __device__ __forceinline__ double block_sum(double v)
     return t;
 }
 
+// lgS(alpha_k) for every topic, once per handle (alpha is fixed after create)
+__global__ void lgs_table_kernel(int K, const double *__restrict__ alpha, double *__restrict__ out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < K) out[k] = lgamma_stirling(alpha[k]);
+}
+cudaError_t launch_lgs_table(int K, const double *alpha, double *out, cudaStream_t st)
+{
+    lgs_table_kernel<<<(K + 127) / 128, 128, 0, st>>>(K, alpha, out);
+    return cudaGetLastError();
+}
+
 // document part: sum_d [ sum_{k: n_dk>0} (lgS(alpha_k + n_dk) - lgS(alpha_k)) - lgS(alphaSum + N_d) ]
+// One warp per document, work proportional to the document's length (not to K): pass 1 builds the
+// shared-memory histogram of z; pass 2 walks the tokens again and the FIRST token of every topic
+// (lowest lane of a match group, earliest 32-token block) takes the topic's count, clears it and adds
+// the term, so the lgamma evaluations run with most lanes active.  Documents are assigned to warps by
+// a fixed stride and the winner of a topic is fixed, so the sum is reproducible.
 __global__ void __launch_bounds__(RED_THREADS)
 ll_doc_kernel(Dims dm, const int64_t *__restrict__ doc_off, const int32_t *__restrict__ z,
-              const double *__restrict__ alpha, double alpha_sum, double *__restrict__ partials)
+              const double *__restrict__ alpha, const double *__restrict__ lgs_alpha, double alpha_sum,
+              double *__restrict__ partials)
 {
     extern __shared__ int32_t s_cnt[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -211,23 +203,28 @@ ll_doc_kernel(Dims dm, const int64_t *__restrict__ doc_off, const int32_t *__res
         const int64_t t0 = doc_off[d], t1 = doc_off[d + 1];
         for (int64_t t = t0 + lane; t < t1; t += 32) atomicAdd(&cnt[z[t]], 1);
         __syncwarp();
-        for (int k = lane; k < dm.K; k += 32) {
-            int c = cnt[k];
-            if (c > 0) {
-                acc += lgamma_stirling(alpha[k] + (double)c) - lgamma_stirling(alpha[k]);
-                cnt[k] = 0;
+        for (int64_t tb = t0; tb < t1; tb += 32) {
+            const bool valid = tb + lane < t1;
+            const int k = valid ? z[tb + lane] : -1 - lane;
+            const unsigned same = __match_any_sync(FULL, k);
+            if (valid && lane == __ffs(same) - 1) {
+                const int c = cnt[k];
+                if (c > 0) {
+                    cnt[k] = 0;
+                    acc += lgamma_stirling(alpha[k] + (double)c) - lgs_alpha[k];
+                }
             }
+            __syncwarp();
         }
         if (lane == 0) acc -= lgamma_stirling(alpha_sum + (double)(t1 - t0));
-        __syncwarp();
     }
     double t = block_sum(acc);
     if (threadIdx.x == 0) partials[blockIdx.x] = t;
 }
 
 cudaError_t launch_ll_doc(const Dims &dm, const int64_t *doc_off, const int32_t *z,
-                          const double *alpha, double alpha_sum, double *partials, int n_partials,
-                          int sm_count, cudaStream_t st)
+                          const double *alpha, const double *lgs_alpha, double alpha_sum, double *partials,
+                          int n_partials, int sm_count, cudaStream_t st)
 {
     (void)sm_count;
     int warps = RED_THREADS / 32;
@@ -239,7 +236,7 @@ cudaError_t launch_ll_doc(const Dims &dm, const int64_t *doc_off, const int32_t 
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    ll_doc_kernel<<<n_partials, warps * 32, smem, st>>>(dm, doc_off, z, alpha, alpha_sum, partials);
+    ll_doc_kernel<<<n_partials, warps * 32, smem, st>>>(dm, doc_off, z, alpha, lgs_alpha, alpha_sum, partials);
     return cudaGetLastError();
 }
 

@@ -190,8 +190,17 @@ phi_segment_kernel(PeerTable pt, uint32_t epoch_seg, Dims dm, const double *__re
     if (k < dm.Ks) {
         const int blocks_per_seg = dm.Vp / PHI_SEGMENTS / PHI_ROW_BLOCK;
         const double *p = partial + (size_t)s * blocks_per_seg * dm.Ks + k;
+        // sequential sum (contract 4.4); eight loads in flight per step so the chain is not latency bound
         double acc = 0.0;
-        for (int b = 0; b < blocks_per_seg; ++b) acc = __dadd_rn(acc, p[(size_t)b * dm.Ks]);
+        int b = 0;
+        for (; b + 8 <= blocks_per_seg; b += 8) {
+            double v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = p[(size_t)(b + i) * dm.Ks];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc = __dadd_rn(acc, v[i]);
+        }
+        for (; b < blocks_per_seg; ++b) acc = __dadd_rn(acc, p[(size_t)b * dm.Ks]);
         if (P2P) {
 #pragma unroll
             for (int q = 0; q < P2P_MAX; ++q)

@@ -91,19 +91,33 @@ __device__ __forceinline__ void scan_scores(const float4 (&a)[NT], const float4 
     rs.S = __shfl_sync(FULL, w, 31);
 }
 
+// Inclusive scan of one tile's 32 lane totals, as the lanes hold it.  GGS keeps it across the tokens of
+// a run: they share the scores, so a token that lands in the tile scanned last (always, when K <= 128)
+// skips the scan -- the same values, computed once.
+struct TileScan {
+    int js;                  // tile the fields belong to, -1 = none
+    float q0, q1, q2;        // the lane's own prefixes inside the tile
+    float inc, prev;         // inclusive scan at this lane and at the lane before (0 for lane 0)
+};
+
 // first k with cumsum_k >= U * sum, searched tile -> lane -> element
-template <int NT>
-__device__ __forceinline__ int draw_topic(const RowScan<NT> &rs, float U, int lane, int K)
+template <int NT, bool REUSE>
+__device__ __forceinline__ int draw_topic(const RowScan<NT> &rs, TileScan &ts, float U, int lane, int K)
 {
     const float u = __fmul_rn(U, rs.S);
-    const unsigned mt = __ballot_sync(FULL, rs.B >= u);
-    int js = (mt ? __ffs(mt) - 1 : 31) >> 2;
-    if (js > NT - 1) js = NT - 1;
-    float base = __shfl_sync(FULL, rs.B, js > 0 ? 4 * js - 1 : 0);
-    if (js == 0) base = 0.0f;
+    int js = 0;
+    float base = 0.0f;
+    if (NT > 1) {
+        const unsigned mt = __ballot_sync(FULL, rs.B >= u);
+        js = (mt ? __ffs(mt) - 1 : 31) >> 2;
+        if (js > NT - 1) js = NT - 1;
+        base = __shfl_sync(FULL, rs.B, js > 0 ? 4 * js - 1 : 0);
+        if (js == 0) base = 0.0f;
+    }
     const float r = __fsub_rn(u, base);
-    // js is warp-uniform: a real branch picks the tile's registers
-    float q0 = rs.p[0][0], q1 = rs.p[0][1], q2 = rs.p[0][2], inc = rs.p[0][3];
+    if (!REUSE || js != ts.js) {
+        // js is warp-uniform: a real branch picks the tile's registers
+        float q0 = rs.p[0][0], q1 = rs.p[0][1], q2 = rs.p[0][2], inc = rs.p[0][3];
 #define LDAGPU_PICK(J)                                                                         \
     case J:                                                                                    \
         if (J < NT) {                                                                          \
@@ -111,26 +125,28 @@ __device__ __forceinline__ int draw_topic(const RowScan<NT> &rs, float U, int la
             q2 = rs.p[J < NT ? J : 0][2]; inc = rs.p[J < NT ? J : 0][3];                        \
         }                                                                                      \
         break;
-    switch (js) {
-        LDAGPU_PICK(1) LDAGPU_PICK(2) LDAGPU_PICK(3) LDAGPU_PICK(4) LDAGPU_PICK(5) LDAGPU_PICK(6) LDAGPU_PICK(7)
-        default: break;
-    }
+        switch (js) {
+            LDAGPU_PICK(1) LDAGPU_PICK(2) LDAGPU_PICK(3) LDAGPU_PICK(4) LDAGPU_PICK(5) LDAGPU_PICK(6) LDAGPU_PICK(7)
+            default: break;
+        }
 #undef LDAGPU_PICK
-    // inclusive scan of the chosen tile's lane totals
+        // inclusive scan of the chosen tile's lane totals
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        float y = __shfl_up_sync(FULL, inc, off);
-        if (lane >= off) inc = __fadd_rn(inc, y);
+        for (int off = 1; off < 32; off <<= 1) {
+            float y = __shfl_up_sync(FULL, inc, off);
+            if (lane >= off) inc = __fadd_rn(inc, y);
+        }
+        float prev = __shfl_up_sync(FULL, inc, 1);
+        if (lane == 0) prev = 0.0f;
+        ts.js = js; ts.q0 = q0; ts.q1 = q1; ts.q2 = q2; ts.inc = inc; ts.prev = prev;
     }
-    const unsigned m = __ballot_sync(FULL, inc >= r);
+    const unsigned m = __ballot_sync(FULL, ts.inc >= r);
     const int ls = m ? __ffs(m) - 1 : 31;
-    float prev = __shfl_up_sync(FULL, inc, 1);
-    if (lane == 0) prev = 0.0f;
-    const float r2 = __fsub_rn(r, prev);
+    const float r2 = __fsub_rn(r, ts.prev);
     int i = 3;
-    if (q2 >= r2) i = 2;
-    if (q1 >= r2) i = 1;
-    if (q0 >= r2) i = 0;
+    if (ts.q2 >= r2) i = 2;
+    if (ts.q1 >= r2) i = 1;
+    if (ts.q0 >= r2) i = 0;
     const int k = __shfl_sync(FULL, TILE * js + 4 * lane + i, ls);
     return k < K ? k : K - 1;
 }
@@ -214,7 +230,7 @@ __global__ void __launch_bounds__(z_warps<NT, PCGS>() * 32, (PCGS && NT == 8) ? 
             d = a.item_doc[item];
             t0 = a.item_begin[item];
             int64_t de = a.doc_off[d + 1];
-            t1 = t0 + GGS_CHUNK < de ? t0 + GGS_CHUNK : de;
+            t1 = t0 + a.chunk < de ? t0 + a.chunk : de;
             const float *trow = a.theta + (size_t)d * Ks;
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
@@ -264,6 +280,8 @@ __global__ void __launch_bounds__(z_warps<NT, PCGS>() * 32, (PCGS && NT == 8) ? 
                 if (rem) request(e);
 
                 RowScan<NT> rs;
+                TileScan ts;
+                ts.js = -1;
                 if (!PCGS) scan_scores<NT>(th, ph, rs, lane);
                 for (int tt = b; tt < e; ++tt) {
                     if (PCGS) {
@@ -281,7 +299,8 @@ __global__ void __launch_bounds__(z_warps<NT, PCGS>() * 32, (PCGS && NT == 8) ? 
                         scan_scores<NT>(aa, ph, rs, lane);
                     }
                     const float Ut = __shfl_sync(FULL, U, tt);
-                    const int k = draw_topic<NT>(rs, Ut, lane, K);
+                    // (at 8 tiles the six extra live registers cost more in spill reloads than the reuse saves)
+                    const int k = draw_topic<NT, !PCGS && NT < 8>(rs, ts, Ut, lane, K);
                     if (lane == tt) znew = k;
                     if (PCGS) {
                         // add it back under its new topic (UncollapsedParallelLDA.java:1535)

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) z_kernel_big(ZArgs a)
         } else {
             t0 = a.item_begin[item];
             const int64_t de = a.doc_off[d + 1];
-            t1 = t0 + GGS_CHUNK < de ? t0 + GGS_CHUNK : de;
+            t1 = t0 + a.chunk < de ? t0 + a.chunk : de;
             const float *trow = a.theta + (size_t)d * Ks;
             for (int k = lane; k < ROWF; k += 32) vec[k] = k < Ks ? trow[k] : 0.0f;
         }
