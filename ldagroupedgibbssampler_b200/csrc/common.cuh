@@ -101,12 +101,18 @@ cudaError_t launch_theta_big(const ThetaArgs &a, int sm_count, cudaStream_t st);
 cudaError_t launch_z_ggs_big(const ZArgs &a, int sm_count, cudaStream_t st);
 cudaError_t launch_z_pcgs_big(const ZArgs &a, int sm_count, cudaStream_t st);
 // sparse PCGS z-step and its alias tables (kernels_sparse.cu)
+// one slot of a type's alias table (util/OptimizedGentleAliasMethod.java:52-79: ps[i], a[i]) -- kept side by
+// side so that building a slot is one 8-byte store and a draw one 8-byte load
+struct __align__(8) AliasSlot {
+    float ps;
+    int32_t alias;
+};
 int64_t alias_scratch_threads(const Dims &dm, int sm_count);
-cudaError_t launch_alias_build(const Dims &dm, const float *alpha, const float *phiT, float *ps, int32_t *al,
+cudaError_t launch_alias_build(const Dims &dm, const float *alpha, const float *phiT, AliasSlot *table,
                                float *type_norm, double *bs_scratch, int32_t *stack_scratch,
                                const int32_t *active, int32_t n_active, int sm_count, cudaStream_t st);
 size_t spalias_list_bytes(const Dims &dm, int max_doc_len, int sm_count);
-cudaError_t launch_z_spalias(const ZArgs &z, const float *ps, const int32_t *al, const float *type_norm,
+cudaError_t launch_z_spalias(const ZArgs &z, const AliasSlot *table, const float *type_norm,
                              int *lists, int max_doc_len, int sm_count, cudaStream_t st);
 // largest K the dense z-step can hold in shared memory (row + vector [+ counts] per warp)
 inline int max_dense_topics(bool pcgs) { return pcgs ? 18000 : 27000; }

@@ -131,8 +131,9 @@ struct ldagpu_handle_s {
     DevBuf<int32_t> tokens, z, n_wk, n_k, item_doc, scratch_i32;
     DevBuf<float> phiT, theta, alpha_f;
     // sparse scheme: per-type alias tables over alpha_k * phi_kw and the build scratch
-    DevBuf<float> alias_ps, type_norm;
-    DevBuf<int32_t> alias_al, alias_stack, active_types, sparse_lists;
+    DevBuf<float> type_norm;
+    DevBuf<AliasSlot> alias_table;
+    DevBuf<int32_t> alias_stack, active_types, sparse_lists;
     int32_t n_active_types = 0;
     DevBuf<double> alias_bs;
     int max_doc_len = 0;
@@ -242,7 +243,7 @@ int step_z(ldagpu_handle h, bool fused = false)
         if (!h->theta.p) return h->fail("GGS z-step needs theta: call ldagpu_sample_theta or ldagpu_set_theta first");
         CK(h, launch_z_ggs(a, h->sm_count, h->stream));
     } else if (h->scheme == LDAGPU_SCHEME_SPALIAS) {
-        CK(h, launch_z_spalias(a, h->alias_ps.p, h->alias_al.p, h->type_norm.p, h->sparse_lists.p, h->max_doc_len,
+        CK(h, launch_z_spalias(a, h->alias_table.p, h->type_norm.p, h->sparse_lists.p, h->max_doc_len,
                                h->sm_count, h->stream));
     } else {
         CK(h, launch_z_pcgs(a, h->sm_count, h->stream));
@@ -255,7 +256,7 @@ int step_z(ldagpu_handle h, bool fused = false)
 int step_alias(ldagpu_handle h)
 {
     if (h->scheme != LDAGPU_SCHEME_SPALIAS) return 0;
-    CK(h, launch_alias_build(h->dm, h->alpha_f.p, h->phiT.p, h->alias_ps.p, h->alias_al.p, h->type_norm.p,
+    CK(h, launch_alias_build(h->dm, h->alpha_f.p, h->phiT.p, h->alias_table.p, h->type_norm.p,
                              h->alias_bs.p, h->alias_stack.p, h->active_types.p, h->n_active_types, h->sm_count,
                              h->stream));
     h->last_launches += 1;
@@ -677,8 +678,7 @@ int ldagpu_create(int32_t K, int32_t V, int64_t D, const int64_t *doc_offsets, c
             h->max_doc_len = (int)std::max<int64_t>(h->max_doc_len, doc_offsets[d + 1] - doc_offsets[d]);
         if (scheme == LDAGPU_SCHEME_SPALIAS) {
             const size_t T = (size_t)alias_scratch_threads(dm, h->sm_count);
-            CK(h, h->alias_ps.alloc((size_t)dm.Vp * dm.Ks));
-            CK(h, h->alias_al.alloc((size_t)dm.Vp * dm.Ks));
+            CK(h, h->alias_table.alloc((size_t)dm.Vp * dm.Ks));
             CK(h, h->type_norm.alloc((size_t)dm.Vp));
             CK(h, h->alias_bs.alloc(T * (size_t)K));
             CK(h, h->alias_stack.alloc(T * (size_t)K));
@@ -694,8 +694,7 @@ int ldagpu_create(int32_t K, int32_t V, int64_t D, const int64_t *doc_offsets, c
             CK(h, h->active_types.alloc(std::max<size_t>(act.size(), 1)));
             if (!act.empty())
                 CK(h, cudaMemcpy(h->active_types.p, act.data(), sizeof(int32_t) * act.size(), cudaMemcpyHostToDevice));
-            CK(h, cudaMemset(h->alias_ps.p, 0, sizeof(float) * h->alias_ps.n));
-            CK(h, cudaMemset(h->alias_al.p, 0, sizeof(int32_t) * h->alias_al.n));
+            CK(h, cudaMemset(h->alias_table.p, 0, sizeof(AliasSlot) * h->alias_table.n));
             CK(h, cudaMemset(h->type_norm.p, 0, sizeof(float) * h->type_norm.n));
         }
         CK(h, cudaMemcpy(h->doc_off.p, doc_offsets, sizeof(int64_t) * ((size_t)D + 1), cudaMemcpyHostToDevice));
@@ -743,7 +742,7 @@ int ldagpu_destroy(ldagpu_handle h)
     h->alpha_f.release(); h->alpha_d.release(); h->lgs_alpha.release(); h->partial.release(); h->seg.release(); h->topic_sum.release();
     h->phi_mean.release(); h->red.release(); h->red_out.release(); h->scratch_f64.release();
     h->counter.release(); h->bad.release();
-    h->alias_ps.release(); h->type_norm.release(); h->alias_al.release(); h->alias_stack.release(); h->alias_bs.release();
+    h->alias_table.release(); h->type_norm.release(); h->alias_stack.release(); h->alias_bs.release();
     h->active_types.release(); h->sparse_lists.release();
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;

@@ -13,7 +13,7 @@
 //   phi_draw      g = Gamma(beta + n_wk) in fp64, stored rounded to fp32; fp64 partial column sums
 //                 over blocks of 8 words (sequential within the block)
 //   phi_segments  the blocks of each of the 8 vocabulary segments summed sequentially
-//   phi_normalise S_k = ((s0+s1)+(s2+s3))+((s4+s5)+(s6+s7)); phi = (float)(g / S_k), floored
+//   phi_normalise S_k = ((s0+s1)+(s2+s3))+((s4+s5)+(s6+s7)); phi = (float)(g * (1 / S_k)), floored
 // The fixed summation tree makes the result independent of the grid and of the number of GPUs
 // (rank r owns segments [8r/G, 8(r+1)/G)).
 #include "common.cuh"
@@ -255,12 +255,13 @@ phi_normalise_kernel(PeerTable pt, uint32_t epoch_seg, uint32_t epoch_phi, Dims 
         const double S = __dadd_rn(__dadd_rn(__dadd_rn(s[0], s[1]), __dadd_rn(s[2], s[3])),
                                    __dadd_rn(__dadd_rn(s[4], s[5]), __dadd_rn(s[6], s[7])));
         if (blockIdx.y == 0 && topic_sum) topic_sum[k] = S;
+        const double invS = S != 0.0 ? __ddiv_rn(1.0, S) : 0.0;   // one reciprocal per topic, one product per cell
         const int32_t wa = row0 + blockIdx.y * NORM_ROWS;
         for (int32_t w = wa; w < wa + NORM_ROWS && w < row1 && w < dm.V; ++w) {
             const size_t idx = (size_t)w * dm.Ks + k;
             float v = phiT[idx];
             if (S != 0.0) {
-                v = __double2float_rn(__ddiv_rn((double)v, S));
+                v = __double2float_rn(__dmul_rn((double)v, invS));
                 if (v <= 0.0f) v = 0x1p-149f;   // ParallelDirichlet.java:63-65 floors at Double.MIN_VALUE
                 if (!P2P) phiT[idx] = v;
             }

@@ -31,7 +31,7 @@ constexpr unsigned FULL = 0xffffffffu;
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 alias_build_kernel(Dims dm, const float *__restrict__ alpha, const float *__restrict__ phiT,
-                   float *__restrict__ ps, int32_t *__restrict__ al, float *__restrict__ type_norm,
+                   AliasSlot *__restrict__ table, float *__restrict__ type_norm,
                    double *__restrict__ bs_all, int32_t *__restrict__ stack_all,
                    const int32_t *__restrict__ active, int32_t n_active)
 {
@@ -49,8 +49,7 @@ alias_build_kernel(Dims dm, const float *__restrict__ alpha, const float *__rest
             if (base + j >= n_active) break;
             const int64_t w = active[base + j];
             const float *ph = phiT + (size_t)w * dm.Ks;
-            float *pw = ps + (size_t)w * dm.Ks;
-            int32_t *aw = al + (size_t)w * dm.Ks;
+            AliasSlot *tw = table + (size_t)w * dm.Ks;
             double *bs = bs_all + (size_t)(warp_first + j) * K;
             int32_t *stack = stack_all + (size_t)(warp_first + j) * K;
             double acc = 0.0;
@@ -67,8 +66,7 @@ alias_build_kernel(Dims dm, const float *__restrict__ alpha, const float *__rest
                 if (valid) {
                     b = __dsub_rn(__ddiv_rn((double)__fmul_rn(alpha[i], ph[i]), norm), k1);
                     bs[i] = b;
-                    aw[i] = i;
-                    pw[i] = 0.0f;
+                    tw[i] = AliasSlot{0.0f, i};
                 }
                 const bool is_low = valid && b < 0.0;
                 const unsigned lm = __ballot_sync(FULL, is_low), hm = __ballot_sync(FULL, valid && !is_low);
@@ -83,8 +81,7 @@ alias_build_kernel(Dims dm, const float *__restrict__ alpha, const float *__rest
         // ---- phase B
         if (base + lane < n_active) {
             const int64_t w = active[base + lane];
-            float *pw = ps + (size_t)w * dm.Ks;
-            int32_t *aw = al + (size_t)w * dm.Ks;
+            AliasSlot *tw = table + (size_t)w * dm.Ks;
             double *bs = bs_all + (size_t)tid * K;
             int32_t *stack = stack_all + (size_t)tid * K;
             // low stack: stack[0..low), high stack: stack[K-high..K) (top = K-high).  The reference loop
@@ -106,8 +103,7 @@ alias_build_kernel(Dims dm, const float *__restrict__ alpha, const float *__rest
                 d = nb;
                 if (nb <= 0.0) { high--; have_h = false; }
                 if (nb < 0.0) { pending = true; pl = h; pc = nb; }
-                aw[l] = h;
-                pw[l] = __double2float_rn(__dadd_rn(1.0, __dmul_rn((double)K, c)));
+                tw[l] = AliasSlot{__double2float_rn(__dadd_rn(1.0, __dmul_rn((double)K, c))), h};
             }
         }
         __syncwarp();
@@ -116,12 +112,15 @@ alias_build_kernel(Dims dm, const float *__restrict__ alpha, const float *__rest
 
 int64_t alias_scratch_threads(const Dims &dm, int sm_count)
 {
-    int64_t t = (int64_t)sm_count * 512;
+#ifndef ALIAS_TPS
+#define ALIAS_TPS 512
+#endif
+    int64_t t = (int64_t)sm_count * ALIAS_TPS;
     int64_t need = ((int64_t)dm.V + 127) / 128 * 128;
     return need < t ? need : t;
 }
 
-cudaError_t launch_alias_build(const Dims &dm, const float *alpha, const float *phiT, float *ps, int32_t *al,
+cudaError_t launch_alias_build(const Dims &dm, const float *alpha, const float *phiT, AliasSlot *table,
                                float *type_norm, double *bs_scratch, int32_t *stack_scratch,
                                const int32_t *active, int32_t n_active, int sm_count, cudaStream_t st)
 {
@@ -131,7 +130,7 @@ cudaError_t launch_alias_build(const Dims &dm, const float *alpha, const float *
     const int64_t rounds = ((int64_t)n_active + T - 1) / T;
     int64_t blocks = (((int64_t)n_active + rounds - 1) / rounds + 127) / 128;
     if (blocks > T / 128) blocks = T / 128;
-    alias_build_kernel<<<(unsigned)blocks, 128, 0, st>>>(dm, alpha, phiT, ps, al, type_norm, bs_scratch,
+    alias_build_kernel<<<(unsigned)blocks, 128, 0, st>>>(dm, alpha, phiT, table, type_norm, bs_scratch,
                                                        stack_scratch, active, n_active);
     return cudaGetLastError();
 }
@@ -144,8 +143,7 @@ cudaError_t launch_alias_build(const Dims &dm, const float *alpha, const float *
 // ---------------------------------------------------------------------------------------
 struct SparseArgs {
     ZArgs z;
-    const float *ps;
-    const int32_t *al;
+    const AliasSlot *table;
     const float *type_norm;
     int *lists;   // per resident warp: nz[cap], cnt[cap], cum[cap] in global memory (L1/L2 resident)
     int cap;      // list capacity per warp (multiple of 32)
@@ -265,7 +263,8 @@ __global__ void __launch_bounds__(256) z_spalias_kernel(SparseArgs sa)
                     int i = __float2int_rz(ups);
                     if (i > K - 1) i = K - 1;
                     const size_t cell = (size_t)wt * Ks + i;
-                    if (__fsub_rn(ups, __int2float_rn(i)) > __ldg(sa.ps + cell)) i = __ldg(sa.al + cell);
+                    const int2 slot = __ldg(reinterpret_cast<const int2 *>(sa.table + cell));   // {ps, alias}
+                    if (__fsub_rn(ups, __int2float_rn(i)) > __int_as_float(slot.x)) i = slot.y;
                     nw = i;
                 } else {
                     // likelihood part: first slot with u*tot - tn <= cum (:269-275, findIdx :347-375)
@@ -305,12 +304,12 @@ size_t spalias_list_bytes(const Dims &dm, int max_doc_len, int sm_count)
     return (size_t)sm_count * 8 * 8 * (size_t)cap * 12;   // up to 8 CTAs of 8 warps per SM
 }
 
-cudaError_t launch_z_spalias(const ZArgs &z, const float *ps, const int32_t *al, const float *type_norm,
+cudaError_t launch_z_spalias(const ZArgs &z, const AliasSlot *table, const float *type_norm,
                              int *lists, int max_doc_len, int sm_count, cudaStream_t st)
 {
     if (z.n_items == 0) return cudaSuccess;
     SparseArgs sa;
-    sa.z = z; sa.ps = ps; sa.al = al; sa.type_norm = type_norm; sa.lists = lists;
+    sa.z = z; sa.table = table; sa.type_norm = type_norm; sa.lists = lists;
     int cap = max_doc_len < z.dm.K ? max_doc_len : z.dm.K;
     sa.cap = (cap + 32 + 31) / 32 * 32;
     int per_sm = 1;

@@ -621,7 +621,7 @@ void oracle_z_pcgs_faithful(int64_t D, const int64_t *doc_off, const int32_t *to
  * fp32; per-topic sum S_k in fp64 over the ROUNDED values in a fixed three-level order:
  *   row blocks of 8 words summed sequentially, blocks of one of 8 vocabulary segments summed
  *   sequentially, the 8 segment sums combined as ((0+1)+(2+3))+((4+5)+(6+7));
- * phi = (float)(g32 / S_k), floored at the smallest fp32 subnormal.
+ * phi = (float)(g32 * (1 / S_k)), floored at the smallest fp32 subnormal.
  * Reference: topics/LDAGroupedGibbsSampler.java:182-192, topics/LDAPartiallyCollapsedGibbsSampler.java:91-101,
  * types/ParallelDirichlet.java:46-70; the initial Phi of every scheme:
  * topics/UncollapsedParallelLDA.java:1287-1294 + types/MarsagliaSparseDirichlet.java:31-55.
@@ -666,7 +666,8 @@ void oracle_phi_contract(int32_t V, int32_t K, const int32_t *n_wk, double beta,
     for (int64_t w = 0; w < V; ++w)
         for (int k = 0; k < K; ++k) {
             if (S[k] == 0.0) continue;
-            float v = (float)((double)phiT[(size_t)w * K + k] / S[k]);
+            /* one reciprocal per topic, one product per cell (contract 4.4) */
+            float v = (float)((double)phiT[(size_t)w * K + k] * (1.0 / S[k]));
             phiT[(size_t)w * K + k] = (v <= 0.0f) ? F32_TRUE_MIN : v;
         }
     free(S);
