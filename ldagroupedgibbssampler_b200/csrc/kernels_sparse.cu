@@ -138,36 +138,222 @@ cudaError_t launch_alias_build(const Dims &dm, const float *alpha, const float *
 
 // ---------------------------------------------------------------------------------------
 // Sparse z-step.  One warp per document (PCGS is sequential inside a document).  The document's
-// non-zero topics live in a per-warp shared-memory list in the reference's order (append on first
-// use, swap-remove when a count reaches 0), with their counts beside them.
+// non-zero topics and their counts form a list in the reference's order (append on first use,
+// swap-remove when a count reaches 0).  The list is cut into blocks of 256 entries and lane l owns
+// entries 8l..8l+7 of a block (two 16-byte loads per array): finding a topic, gathering Phi at the
+// listed topics, the cumulative sum (lane-local prefix + one warp scan per block) and the search all
+// work on those eight registers.
+//   fast path  lists of up to 256 topics live in shared memory (2 KB per warp, 64 warps per SM);
+//   slow path  a document whose list outgrows that continues on per-warp lists in global memory with
+//              the same arithmetic block by block (early sweeps from a random start, very long documents).
 // ---------------------------------------------------------------------------------------
+constexpr int SP_BLOCK = 256;   // list entries per block (8 per lane)
+constexpr int SP_WARPS = 8;     // warps per CTA
+
 struct SparseArgs {
     ZArgs z;
     const AliasSlot *table;
     const float *type_norm;
-    int *lists;   // per resident warp: nz[cap], cnt[cap], cum[cap] in global memory (L1/L2 resident)
-    int cap;      // list capacity per warp (multiple of 32)
+    int *lists;   // per resident warp: nz[cap], cnt[cap], cum[cap] in global memory (slow path)
+    int cap;      // list capacity per warp (multiple of SP_BLOCK)
 };
 
+__device__ __forceinline__ void load8(const int *a, int (&v)[8])
+{
+    const int4 x = reinterpret_cast<const int4 *>(a)[0], y = reinterpret_cast<const int4 *>(a)[1];
+    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+}
+
+// position of topic k in the list, -1 if absent
+template <bool MULTI>
 __device__ __forceinline__ int list_find(const int *nz, int nnz, int k, int lane)
 {
-    for (int c0 = 0; c0 < nnz; c0 += 32) {
-        const int i = c0 + lane;
-        const unsigned m = __ballot_sync(FULL, i < nnz && nz[i] == k);
-        if (m) return c0 + __ffs(m) - 1;
+    for (int b0 = 0; b0 < (MULTI ? nnz : 1); b0 += SP_BLOCK) {
+        int v[8];
+        load8(nz + b0 + 8 * lane, v);
+        const int nvalid = nnz - (b0 + 8 * lane);
+        int pe = -1;
+#pragma unroll
+        for (int e = 7; e >= 0; --e)
+            if (e < nvalid && v[e] == k) pe = e;
+        const unsigned m = __ballot_sync(FULL, pe >= 0);
+        if (m) {
+            const int l = __ffs(m) - 1;
+            return b0 + 8 * l + __shfl_sync(FULL, pe, l);
+        }
     }
     return -1;
 }
 
-__global__ void __launch_bounds__(256) z_spalias_kernel(SparseArgs sa)
+// add one token of topic k (SpaliasUncollapsedParallelLDA.java:223-230,306-312); pos = its list position when known
+__device__ __forceinline__ void list_add_at(int *nz, int *cnt, int &nnz, int k, int pos, int lane)
+{
+    const int c = pos >= 0 ? cnt[pos] : 0;
+    __syncwarp();
+    if (lane == 0) {
+        if (pos < 0) { nz[nnz] = k; cnt[nnz] = 1; }
+        else cnt[pos] = c + 1;
+    }
+    if (pos < 0) ++nnz;
+    __syncwarp();
+}
+
+// remove one token of topic `old` (:159-166, :295-304)
+template <bool MULTI>
+__device__ __forceinline__ void list_remove(int *nz, int *cnt, int &nnz, int old, int lane)
+{
+    const int pos = list_find<MULTI>(nz, nnz, old, lane);
+    const int c = cnt[pos] - 1;
+    const int lk = nz[nnz - 1], lc = cnt[nnz - 1];
+    __syncwarp();
+    if (lane == 0) {
+        if (c == 0) { nz[pos] = lk; cnt[pos] = lc; }
+        else cnt[pos] = c;
+    }
+    if (c == 0) --nnz;
+    __syncwarp();
+}
+
+// One token: scores over the list, cumulative sum, prior/likelihood branch.  Returns the new topic and, in
+// `slot`, its list position when the likelihood branch found it (-1 otherwise).
+template <bool MULTI>
+__device__ __forceinline__ int sparse_draw(const SparseArgs &sa, const int *nz, const int *cnt, float *cum, int nnz,
+                                           int wt, float u, int lane, int &slot)
+{
+    const int K = sa.z.dm.K, Ks = sa.z.dm.Ks;
+    const float *ph = sa.z.phiT + (size_t)wt * Ks;
+    const float tn = __ldg(sa.type_norm + wt);
+    float carry = 0.0f, E = 0.0f;
+    float q[8];
+    int nvalid0 = 0;
+    for (int b0 = 0; b0 < (MULTI ? nnz : 1); b0 += SP_BLOCK) {
+        int kk[8], cc[8];
+        load8(nz + b0 + 8 * lane, kk);
+        load8(cnt + b0 + 8 * lane, cc);
+        const int nvalid = nnz - (b0 + 8 * lane);
+        float s[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[e] = e < nvalid ? __ldg(ph + kk[e]) : 0.0f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[e] = e < nvalid ? __fmul_rn(__int2float_rn(cc[e]), s[e]) : 0.0f;
+        q[0] = s[0];
+#pragma unroll
+        for (int e = 1; e < 8; ++e) q[e] = __fadd_rn(q[e - 1], s[e]);
+        float inc = q[7];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const float y = __shfl_up_sync(FULL, inc, off);
+            if (lane >= off) inc = __fadd_rn(inc, y);
+        }
+        E = __shfl_up_sync(FULL, inc, 1);
+        if (lane == 0) E = 0.0f;
+        if (MULTI) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (e < nvalid) cum[b0 + 8 * lane + e] = __fadd_rn(carry, __fadd_rn(E, q[e]));
+        }
+        carry = __fadd_rn(carry, __shfl_sync(FULL, inc, 31));
+        nvalid0 = nvalid;
+    }
+    if (MULTI) __syncwarp();
+    const float sum = carry;
+    const float tot = __fadd_rn(tn, sum);
+    slot = -1;
+    if (u < __fdiv_rn(tn, tot) || nnz == 0) {
+        // prior part: alias draw (:265-267, OptimizedGentleAliasMethod.java:100-107)
+        const float up = __fadd_rn(u, __fdiv_rn(__fmul_rn(sum, u), tn));
+        const float ups = __fmul_rn(up, __int2float_rn(K));
+        int i = __float2int_rz(ups);
+        if (i > K - 1) i = K - 1;
+        const int2 entry = __ldg(reinterpret_cast<const int2 *>(sa.table + (size_t)wt * Ks + i));   // {ps, alias}
+        if (__fsub_rn(ups, __int2float_rn(i)) > __int_as_float(entry.x)) i = entry.y;
+        return i;
+    }
+    // likelihood part: first slot with u*tot - tn <= cum (:269-275, findIdx :347-375)
+    const float ul = __fsub_rn(__fmul_rn(u, tot), tn);
+    slot = nnz - 1;
+    if (!MULTI) {
+        int pe = -1;
+#pragma unroll
+        for (int e = 7; e >= 0; --e)
+            if (e < nvalid0 && ul <= __fadd_rn(E, q[e])) pe = e;
+        const unsigned m = __ballot_sync(FULL, pe >= 0);
+        if (m) {
+            const int l = __ffs(m) - 1;
+            slot = 8 * l + __shfl_sync(FULL, pe, l);
+        }
+    } else {
+        for (int b0 = 0; b0 < nnz; b0 += SP_BLOCK) {
+            const int nvalid = nnz - (b0 + 8 * lane);
+            int pe = -1;
+#pragma unroll
+            for (int e = 7; e >= 0; --e)
+                if (e < nvalid && ul <= cum[b0 + 8 * lane + e]) pe = e;
+            const unsigned m = __ballot_sync(FULL, pe >= 0);
+            if (m) {
+                const int l = __ffs(m) - 1;
+                slot = b0 + 8 * l + __shfl_sync(FULL, pe, l);
+                break;
+            }
+        }
+    }
+    return nz[slot];
+}
+
+// tokens [ta, t1) of one document on the given lists; MULTI = lists of any length (global memory)
+template <bool MULTI>
+__device__ __forceinline__ int64_t sparse_tokens(const SparseArgs &sa, int *nz, int *cnt, float *cum, int &nnz,
+                                                 int64_t ta, int64_t t1, int lane)
 {
     const ZArgs &a = sa.z;
+    const int Ks = a.dm.Ks;
+    for (int64_t tb = ta; tb < t1; tb += 32) {
+        const int64_t t = tb + lane;
+        const bool valid = t < t1;
+        const int nv = (int)((t1 - tb) < 32 ? (t1 - tb) : 32);
+        const int w = valid ? a.tokens[t] : 0;
+        const int zold = valid ? a.z[t] : 0;
+        float U = 0.0f;
+        if (valid) {
+            const unsigned long long gt = (unsigned long long)(a.dm.token_base + t);
+            const uint4 r = philox4x32_10((uint32_t)gt, (uint32_t)(gt >> 32), a.sweep, STREAM_Z << 24, a.seed_lo, a.seed_hi);
+            U = uniform23(r.x);
+        }
+        int znew = 0, done = nv;
+        for (int tt = 0; tt < nv; ++tt) {
+            if (!MULTI && nnz >= SP_BLOCK) { done = tt; break; }   // the list may outgrow shared memory: hand over
+            const int wt = __shfl_sync(FULL, w, tt);
+            const int old = __shfl_sync(FULL, zold, tt);
+            const float u = __shfl_sync(FULL, U, tt);
+            list_remove<MULTI>(nz, cnt, nnz, old, lane);
+            int slot;
+            const int nw = sparse_draw<MULTI>(sa, nz, cnt, cum, nnz, wt, u, lane, slot);
+            if (lane == tt) znew = nw;
+            if (slot < 0) slot = list_find<MULTI>(nz, nnz, nw, lane);
+            list_add_at(nz, cnt, nnz, nw, slot, lane);
+        }
+        if (lane < done) {
+            a.z[t] = znew;
+            if (a.n_wk_out) atomicAdd(&a.n_wk_out[(size_t)w * Ks + znew], 1);
+        }
+        if (done < nv) return tb + done;   // first token not processed
+    }
+    return t1;
+}
+
+// 4 CTAs (32 warps, 64 registers) per SM: 5, 6 and 8 CTAs were measured slower on B200 (spills; the kernel is
+// bound by the DRAM sectors of the Phi gathers, not by latency)
+__global__ void __launch_bounds__(SP_WARPS * 32, 4) z_spalias_kernel(SparseArgs sa)
+{
+    __shared__ __align__(16) int s_nz[SP_WARPS][SP_BLOCK];
+    __shared__ __align__(16) int s_cnt[SP_WARPS][SP_BLOCK];
+    const ZArgs &a = sa.z;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int K = a.dm.K, Ks = a.dm.Ks, cap = sa.cap;
-    // the lists are private to the warp; __syncwarp() orders lane 0's updates before the other lanes' reads
-    int *nz = sa.lists + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * (size_t)cap * 3;
-    int *cnt = nz + cap;
-    float *cum = reinterpret_cast<float *>(cnt + cap);
+    const int cap = sa.cap;
+    int *gnz = sa.lists + ((size_t)blockIdx.x * SP_WARPS + warp) * (size_t)cap * 3;
+    int *gcnt = gnz + cap;
+    float *gcum = reinterpret_cast<float *>(gcnt + cap);
+    int *nz = s_nz[warp], *cnt = s_cnt[warp];
 
     for (;;) {
         unsigned long long item = 0;
@@ -178,121 +364,37 @@ __global__ void __launch_bounds__(256) z_spalias_kernel(SparseArgs sa)
         if (t0 == t1) continue;
         // non-zero topic list in first-occurrence order (SpaliasUncollapsedParallelLDA.java:147-153)
         int nnz = 0;
-        for (int64_t tb = t0; tb < t1; tb += 32) {
+        bool in_smem = true;
+        for (int64_t tb = t0; tb < t1 && in_smem; tb += 32) {
             const int zz = (tb + lane < t1) ? a.z[tb + lane] : -1;
             const int nv = (int)((t1 - tb) < 32 ? (t1 - tb) : 32);
             for (int tt = 0; tt < nv; ++tt) {
                 const int k = __shfl_sync(FULL, zz, tt);
-                const int i = list_find(nz, nnz, k, lane);
-                if (lane == 0) {
-                    if (i < 0) { nz[nnz] = k; cnt[nnz] = 1; }
-                    else cnt[i] += 1;
-                }
-                if (i < 0) ++nnz;
-                __syncwarp();
+                const int pos = list_find<false>(nz, nnz, k, lane);
+                if (pos < 0 && nnz >= SP_BLOCK) { in_smem = false; break; }
+                list_add_at(nz, cnt, nnz, k, pos, lane);
             }
         }
-
-        for (int64_t tb = t0; tb < t1; tb += 32) {
-            const int64_t t = tb + lane;
-            const bool valid = t < t1;
-            const int nv = (int)((t1 - tb) < 32 ? (t1 - tb) : 32);
-            const int w = valid ? a.tokens[t] : 0;
-            const int zold = valid ? a.z[t] : 0;
-            float U = 0.0f;
-            if (valid) {
-                unsigned long long gt = (unsigned long long)(a.dm.token_base + t);
-                uint4 r = philox4x32_10((uint32_t)gt, (uint32_t)(gt >> 32), a.sweep, STREAM_Z << 24, a.seed_lo, a.seed_hi);
-                U = uniform23(r.x);
-            }
-            int znew = 0;
-            for (int tt = 0; tt < nv; ++tt) {
-                const int wt = __shfl_sync(FULL, w, tt);
-                const int old = __shfl_sync(FULL, zold, tt);
-                const float u = __shfl_sync(FULL, U, tt);
-                const float *ph = a.phiT + (size_t)wt * Ks;
-                // remove the token from its topic (:159-166, :295-304)
-                {
-                    const int i = list_find(nz, nnz, old, lane);
-                    bool emptied = false;
-                    if (lane == 0) {
-                        const int c = cnt[i] - 1;
-                        cnt[i] = c;
-                        if (c == 0) { nz[i] = nz[nnz - 1]; cnt[i] = cnt[nnz - 1]; emptied = true; }
-                    }
-                    emptied = __shfl_sync(FULL, emptied, 0);
-                    if (emptied) --nnz;
-                    __syncwarp();
-                }
-                // sparse cumulative sum over the list (:178-191), chunks of 32 with sequential carries
-                float carry = 0.0f;
-                for (int g0 = 0; g0 < nnz; g0 += 128) {
-                    // four chunks at a time: all gathers are issued before the first scan needs one
-                    float xs[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int i = g0 + 32 * c + lane;
-                        xs[c] = i < nnz ? __fmul_rn(__int2float_rn(cnt[i]), __ldg(ph + nz[i])) : 0.0f;
-                    }
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int c0 = g0 + 32 * c;
-                        if (c0 < nnz) {
-                            const int i = c0 + lane;
-                            float x = xs[c];
-#pragma unroll
-                            for (int off = 1; off < 32; off <<= 1) {
-                                const float y = __shfl_up_sync(FULL, x, off);
-                                if (lane >= off) x = __fadd_rn(x, y);
-                            }
-                            const float cv = c0 == 0 ? x : __fadd_rn(carry, x);
-                            if (i < nnz) cum[i] = cv;
-                            carry = __shfl_sync(FULL, cv, 31);
-                        }
-                    }
-                }
+        int64_t next = t0;
+        if (in_smem) next = sparse_tokens<false>(sa, nz, cnt, nullptr, nnz, t0, t1, lane);
+        if (next < t1) {
+            // slow path: continue (or, when the initial list did not fit, start over) on the global lists
+            if (in_smem) {
+                for (int i = lane; i < nnz; i += 32) { gnz[i] = nz[i]; gcnt[i] = cnt[i]; }
                 __syncwarp();
-                const float sum = carry;
-                const float tn = __ldg(sa.type_norm + wt);
-                const float tot = __fadd_rn(tn, sum);
-                int nw;
-                if (u < __fdiv_rn(tn, tot) || nnz == 0) {
-                    // prior part: alias draw (:265-267, OptimizedGentleAliasMethod.java:100-107)
-                    const float up = __fadd_rn(u, __fdiv_rn(__fmul_rn(sum, u), tn));
-                    const float ups = __fmul_rn(up, __int2float_rn(K));
-                    int i = __float2int_rz(ups);
-                    if (i > K - 1) i = K - 1;
-                    const size_t cell = (size_t)wt * Ks + i;
-                    const int2 slot = __ldg(reinterpret_cast<const int2 *>(sa.table + cell));   // {ps, alias}
-                    if (__fsub_rn(ups, __int2float_rn(i)) > __int_as_float(slot.x)) i = slot.y;
-                    nw = i;
-                } else {
-                    // likelihood part: first slot with u*tot - tn <= cum (:269-275, findIdx :347-375)
-                    const float ul = __fsub_rn(__fmul_rn(u, tot), tn);
-                    int slot = nnz - 1;
-                    for (int c0 = 0; c0 < nnz; c0 += 32) {
-                        const int i = c0 + lane;
-                        const unsigned m = __ballot_sync(FULL, i < nnz && ul <= cum[i]);
-                        if (m) { slot = c0 + __ffs(m) - 1; break; }
+            } else {
+                nnz = 0;
+                for (int64_t tb = t0; tb < t1; tb += 32) {
+                    const int zz = (tb + lane < t1) ? a.z[tb + lane] : -1;
+                    const int nv = (int)((t1 - tb) < 32 ? (t1 - tb) : 32);
+                    for (int tt = 0; tt < nv; ++tt) {
+                        const int k = __shfl_sync(FULL, zz, tt);
+                        const int pos = list_find<true>(gnz, nnz, k, lane);
+                        list_add_at(gnz, gcnt, nnz, k, pos, lane);
                     }
-                    nw = nz[slot];
-                }
-                if (lane == tt) znew = nw;
-                // add the token under its new topic (:223-230, :306-312)
-                {
-                    const int i = list_find(nz, nnz, nw, lane);
-                    if (lane == 0) {
-                        if (i < 0) { nz[nnz] = nw; cnt[nnz] = 1; }
-                        else cnt[i] += 1;
-                    }
-                    if (i < 0) ++nnz;
-                    __syncwarp();
                 }
             }
-            if (valid) {
-                a.z[t] = znew;
-                if (a.n_wk_out) atomicAdd(&a.n_wk_out[(size_t)w * Ks + znew], 1);
-            }
+            sparse_tokens<true>(sa, gnz, gcnt, gcum, nnz, next, t1, lane);
         }
     }
 }
@@ -300,8 +402,8 @@ __global__ void __launch_bounds__(256) z_spalias_kernel(SparseArgs sa)
 size_t spalias_list_bytes(const Dims &dm, int max_doc_len, int sm_count)
 {
     int cap = max_doc_len < dm.K ? max_doc_len : dm.K;
-    cap = (cap + 32 + 31) / 32 * 32;
-    return (size_t)sm_count * 8 * 8 * (size_t)cap * 12;   // up to 8 CTAs of 8 warps per SM
+    cap = (cap + 1 + SP_BLOCK - 1) / SP_BLOCK * SP_BLOCK + SP_BLOCK;   // whole blocks are loaded
+    return (size_t)sm_count * 8 * SP_WARPS * (size_t)cap * 12;   // up to 8 CTAs of 8 warps per SM
 }
 
 cudaError_t launch_z_spalias(const ZArgs &z, const AliasSlot *table, const float *type_norm,
@@ -311,16 +413,16 @@ cudaError_t launch_z_spalias(const ZArgs &z, const AliasSlot *table, const float
     SparseArgs sa;
     sa.z = z; sa.table = table; sa.type_norm = type_norm; sa.lists = lists;
     int cap = max_doc_len < z.dm.K ? max_doc_len : z.dm.K;
-    sa.cap = (cap + 32 + 31) / 32 * 32;
+    sa.cap = (cap + 1 + SP_BLOCK - 1) / SP_BLOCK * SP_BLOCK + SP_BLOCK;
     int per_sm = 1;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, z_spalias_kernel, 256, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, z_spalias_kernel, SP_WARPS * 32, 0);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
     int64_t grid = (int64_t)sm_count * per_sm;
-    const int64_t need = (z.n_items + 7) / 8;
+    const int64_t need = (z.n_items + SP_WARPS - 1) / SP_WARPS;
     if (need < grid) grid = need;
-    z_spalias_kernel<<<(unsigned)grid, 256, 0, st>>>(sa);
+    z_spalias_kernel<<<(unsigned)grid, SP_WARPS * 32, 0, st>>>(sa);
     return cudaGetLastError();
 }
 

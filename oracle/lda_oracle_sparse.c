@@ -100,8 +100,9 @@ static inline float z_uniform23(uint64_t seed, uint64_t token, uint32_t sweep)
 
 /* Sparse z-step, contract.  Per token of a document, in order:
  *   remove the token from its topic (swap-remove from the list when the count reaches 0);
- *   s_i = float(cnt_i) * phiT[w][nz_i] over the list in list order; cumulative sums in chunks of 32
- *   entries (Kogge-Stone inside a chunk, chunk carries added sequentially); sum = last;
+ *   s_i = float(cnt_i) * phiT[w][nz_i] over the list in list order; cumulative sums in blocks of 256
+ *   entries (8 consecutive entries per lane: lane-local prefix, Kogge-Stone over the 32 lane totals,
+ *   block carries added sequentially); sum = last carry;
  *   u ~ U(0,1); tot = tn + sum; if u < tn / tot: alias draw with u' = u + (sum*u)/tn
  *   else: first i with u*tot - tn <= cum_i (last entry if none);
  *   add the token to its new topic (append to the list when it was 0). */
@@ -113,7 +114,7 @@ void oracle_z_spalias_contract(int64_t D, const int64_t *doc_off, const int32_t 
     {
         int32_t *nz = (int32_t *)malloc(sizeof(int32_t) * (size_t)(K + 32));
         int32_t *cnt = (int32_t *)malloc(sizeof(int32_t) * (size_t)(K + 32));
-        float *cum = (float *)malloc(sizeof(float) * (size_t)(K + 32));
+        float *cum = (float *)malloc(sizeof(float) * (size_t)(K + 256));
 #pragma omp for schedule(dynamic, 16)
         for (int64_t d = 0; d < D; ++d) {
             int64_t t0 = doc_off[d], t1 = doc_off[d + 1];
@@ -132,17 +133,31 @@ void oracle_z_spalias_contract(int64_t D, const int64_t *doc_off, const int32_t 
                 for (i = 0; i < nnz; ++i) if (nz[i] == old) break;
                 cnt[i]--;
                 if (cnt[i] == 0) { nz[i] = nz[nnz - 1]; cnt[i] = cnt[nnz - 1]; nnz--; } /* :295-304 */
+                /* cumulative sums, contract 4.6: blocks of 256 list entries; lane l of 32 owns entries
+                 * 8l..8l+7 of the block: lane-local sequential prefix q, Kogge-Stone inclusive scan I of the
+                 * 32 lane totals, cum = carry + (I[l-1] + q); the carry moves on by the block total */
                 float carry = 0.0f, sum = 0.0f;
-                for (int c0 = 0; c0 < nnz; c0 += 32) {
-                    float x[32], y[32];
+                for (int b0 = 0; b0 < nnz; b0 += 256) {
+                    float q[32][8], x[32], y[32];
                     for (int l = 0; l < 32; ++l)
-                        x[l] = (c0 + l < nnz) ? (float)cnt[c0 + l] * ph[nz[c0 + l]] : 0.0f;
+                        for (int e = 0; e < 8; ++e) {
+                            int i = b0 + 8 * l + e;
+                            float sv = (i < nnz) ? (float)cnt[i] * ph[nz[i]] : 0.0f;
+                            q[l][e] = (e == 0) ? sv : q[l][e - 1] + sv;
+                        }
+                    for (int l = 0; l < 32; ++l) x[l] = q[l][7];
                     for (int off = 1; off < 32; off <<= 1) {
                         for (int l = 0; l < 32; ++l) y[l] = (l >= off) ? x[l] + x[l - off] : x[l];
                         memcpy(x, y, sizeof x);
                     }
-                    for (int l = 0; l < 32 && c0 + l < nnz; ++l) cum[c0 + l] = (c0 == 0) ? x[l] : carry + x[l];
-                    carry = (c0 == 0) ? x[31] : carry + x[31];
+                    for (int l = 0; l < 32; ++l) {
+                        float E = l > 0 ? x[l - 1] : 0.0f;
+                        for (int e = 0; e < 8; ++e) {
+                            int i = b0 + 8 * l + e;
+                            if (i < nnz) cum[i] = carry + (E + q[l][e]);
+                        }
+                    }
+                    carry = carry + x[31];
                     sum = carry;
                 }
                 const float u = z_uniform23(seed, (uint64_t)(token_base + t), sweep);
