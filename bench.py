@@ -267,8 +267,24 @@ def main():
     wall_ms = (time.perf_counter() - w0) * 1e3
     call_ms, zk_ms, zk_launches, launches = s.getLastCallStats()
     ck = clocks.stop(set(range(world))) if rank == 0 else None
-    dev_ms = all_max(call_ms)
+    need_more = 1.0 if (rank == 0 and (ck.get("samples") or 0) < 3) else 0.0
     wall_ms = all_max(wall_ms)
+    if all_max(need_more) > 0:
+        # the timed region was shorter than nvidia-smi's sampling period (small workloads): sample the clocks
+        # over an untimed repeat of the same sweeps, long enough for a few samples
+        reps = max(args.steps, int(0.8 / max(wall_ms / 1e3 / args.steps, 1e-6)))
+        clocks2 = ClockSampler()
+        barrier()
+        if rank == 0:
+            clocks2.start()
+            time.sleep(0.15)
+        s.sample(reps)
+        barrier()
+        if rank == 0:
+            ck = clocks2.stop(set(range(world)))
+            ck["note"] = (f"timed region ({wall_ms:.1f} ms) shorter than the sampling period: clocks sampled over an "
+                          f"untimed repeat of {reps} sweeps of the same workload")
+    dev_ms = all_max(call_ms)
     zk_ms_per_launch = all_max(zk_ms / max(zk_launches, 1))
     value = n_total * args.steps / (dev_ms / 1e3)
 

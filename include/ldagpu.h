@@ -69,7 +69,8 @@ int ldagpu_comm_init(ldagpu_handle h, int32_t rank, int32_t world, const void *i
 /* how the ranks exchange counts and Phi: 0 = single GPU, 1 = NCCL collectives (reduce-scatter / all-gather
  * around the Phi kernels), 2 = peer memory (default when the GPUs have peer access: the Phi kernels load the
  * other ranks' partial counts and store Phi into every rank's copy over NVLink themselves).  Environment:
- * LDAGPU_EXCHANGE=nccl|p2p forces one; LDAGPU_P2P_TIMEOUT_MS bounds a wait on a dead rank (default 20000).
+ * LDAGPU_EXCHANGE=nccl|p2p forces one; LDAGPU_P2P_TIMEOUT_MS bounds an in-kernel wait on a dead rank (default 60000; host-side skew between the
+ * ranks is absorbed by an NCCL rendezvous at the start of every exchanging call, not by these waits).
  * The stand-in for the reference's shared AtomicInteger[K][V] delta matrix (UPL:102,363-368,1107-1221). */
 int ldagpu_get_exchange_mode(ldagpu_handle h, int32_t *mode);
 

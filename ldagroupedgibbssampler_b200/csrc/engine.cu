@@ -270,6 +270,18 @@ int step_counts_local(ldagpu_handle h)
     return 0;
 }
 
+// Peer-memory mode: the in-kernel waits are bounded (a dead rank must not hang the GPU), so host-side skew
+// between the ranks -- one rank still generating its shard, replaying java.util.Random for a later shard --
+// must not reach them.  Every API call that exchanges starts with one tiny NCCL all-reduce, which waits as
+// long as it takes; after it the ranks are microseconds apart and the flag waits only absorb compute skew.
+int rendezvous(ldagpu_handle h)
+{
+    if (!h->p2p) return 0;
+    NK(h, g_nccl.AllReduce(h->p2p_local.p + P2P_FLAG_KINDS + 1, h->p2p_local.p + P2P_FLAG_KINDS + 1, 1, ncclInt32, ncclSum,
+                           h->comm, h->stream));
+    return 0;
+}
+
 // defer_reduce (peer-memory mode): only announce the partial counts; the Phi draw that follows sums them.
 int step_counts_exchange(ldagpu_handle h, bool defer_reduce)
 {
@@ -385,6 +397,7 @@ int run_sweeps(ldagpu_handle h, int32_t n, bool with_phi, int32_t *done)
     if (done) *done = 0;
     if (n <= 0) return 0;
     if (ensure_events(h, (size_t)n * EV_PER_SWEEP)) return 1;
+    if (rendezvous(h)) return 1;
     int32_t ran = 0;
     for (int32_t s = 0; s < n; ++s) {
         if (h->abort_flag.load(std::memory_order_relaxed)) break;
@@ -538,7 +551,7 @@ int setup_peer_exchange(ldagpu_handle h)
     pt.done_ctr = h->p2p_local.p;
     pt.error = reinterpret_cast<int *>(h->p2p_local.p + P2P_FLAG_KINDS);
     const char *to = getenv("LDAGPU_P2P_TIMEOUT_MS");
-    pt.timeout_ns = (unsigned long long)(to ? std::max(1L, atol(to)) : 20000L) * 1000000ull;
+    pt.timeout_ns = (unsigned long long)(to ? std::max(1L, atol(to)) : 60000L) * 1000000ull;
     if (ok) {
         for (int r = 0; r < G && ok; ++r) {
             if (r == h->rank) {
@@ -799,6 +812,7 @@ int ldagpu_get_exchange_mode(ldagpu_handle h, int32_t *mode)
 
 static int refresh_counts_and_phi(ldagpu_handle h, bool redraw_phi)
 {
+    if (rendezvous(h)) return 1;
     if (step_counts_local(h) || step_counts_exchange(h, redraw_phi)) return 1;
     if (redraw_phi && step_phi(h, false, nullptr, true)) return 1;
     return sync_check(h);
@@ -870,6 +884,7 @@ int ldagpu_sample_phi(ldagpu_handle h)
 {
     NEED(h);
     bool acc = mean_this_iteration(h);
+    if (rendezvous(h)) return 1;
     if (step_phi(h, acc, nullptr)) return 1;
     if (acc) h->n_sampled_phi += 1;
     return sync_check(h);
