@@ -6,9 +6,9 @@ mirror of the reference's sampler interface.  There is no CPU fallback: importin
 but every compute call needs the built library and a CUDA device.
 """
 from ._lib import LdaGpuError, SO_PATH, SYMBOLS, load, synth_corpus  # noqa: F401
-from .corpus import (Alphabet, InstanceList, SHAPES, load_dataset, shard_documents_by_tokens,  # noqa: F401
-                     take_shard)
+from .corpus import (Alphabet, InstanceList, SHAPES, corpus_statistics, load_dataset,  # noqa: F401
+                     shard_documents_by_tokens, take_shard, tfidf_ranking, tokenize)
 from .sampler import GpuLDASampler, LDAConfiguration, SCHEMES, createModel  # noqa: F401
 
 __all__ = ["GpuLDASampler", "LDAConfiguration", "createModel", "InstanceList", "Alphabet", "load_dataset",
-           "synth_corpus", "shard_documents_by_tokens", "take_shard", "SHAPES", "SCHEMES", "LdaGpuError", "load"]
+           "tokenize", "corpus_statistics", "tfidf_ranking", "synth_corpus", "shard_documents_by_tokens", "take_shard", "SHAPES", "SCHEMES", "LdaGpuError", "load"]

@@ -4,8 +4,9 @@ The reference hands the sampler a MALLET ``InstanceList`` whose instances carry 
 of type ids (reference: src/main/java/cc/mallet/util/LDAUtils.java:136-182,233-330).  This module
 holds the minimum of that: an ``InstanceList`` mirror that flattens to CSR (``doc_offsets`` int64[D+1],
 ``tokens`` int32[N]), a reader for the reference's ``name<TAB>label<TAB>text`` files that is enough for
-its bundled bag-of-words corpora, the named benchmark shapes of SURVEY section 8, and the
-token-balanced document sharding of section 8(e).
+corpora (tokenizer classes, stop list, rare-word and TF-IDF pruning as LDAUtils.loadDataset applies
+them), the named benchmark shapes of SURVEY section 8, and the token-balanced document sharding of
+section 8(e).
 """
 from __future__ import annotations
 
@@ -101,17 +102,62 @@ class _CsrDocs(Sequence):
 
 
 _LINE = re.compile(r"^(\S*)[\s,]*([^\t]+)[\s,]*(.*)$")   # LDAUtils.java:236
-_TOKEN = re.compile(r"[^\W_]+", re.UNICODE)
+
+# Unicode general categories as the reference's tokenizers classify code points
+# (pipe/SimpleTokenizerLarge.java:69-119, pipe/NumericAlsoTokenizer.java:59-100,
+#  pipe/KeepConnectorPunctuationTokenizerLarge.java:69-110, pipe/KeepConnectorPunctuationNumericAlsoTokenizer.java:59-100)
+_WORD = {"Ll", "Lu", "Mc", "Me", "Mn", "Lt", "Lm", "Lo"}
+_DELIM = {"Zs", "Zl", "Zp", "Pe", "Pd", "Pc", "Ps", "Pi", "Pf", "Po"}
 
 
-def load_dataset(path: str, stoplist: Optional[Iterable[str]] = None, keep_numbers: bool = True,
-                 alphabet: Optional[Alphabet] = None) -> InstanceList:
-    """Read a ``name<TAB>label<TAB>text`` file (LDAUtils.java:233-330): lower-case, tokenise on
-    non-alphanumerics, drop stop words, first-seen vocabulary order.  Enough for the reference's
-    bundled bag-of-words corpora (cats.txt, small.txt); rare-word pruning, TF-IDF pruning and the
-    connector-punctuation options of SimpleTokenizerLarge are not restated."""
-    stop = set(stoplist or [])
-    il = InstanceList(alphabet=alphabet or Alphabet())
+def tokenize(text: str, stop: Optional[set] = None, keep_numbers: bool = True, keep_connectors: bool = False,
+             max_token_buffer: int = 10000) -> List[str]:
+    """The reference's four tokenizer classes (LDAUtils.initTokenizer, util/LDAUtils.java:532-561) as one
+    function.  Letters and marks build a token; separators and punctuation end it; with ``keep_numbers``
+    decimal digits build tokens too (NumericAlsoTokenizer), with ``keep_connectors`` connector
+    punctuation ("_", category Pc) does (KeepConnectorPunctuation*).  Every other code point -- digits
+    without ``keep_numbers``, control characters such as TAB, symbols -- is skipped WITHOUT ending the
+    token (SimpleTokenizerLarge.java:113-118), so "ab1c" is one token "abc" when numbers are dropped.
+    A finished token is dropped when the stop list contains it.  A token longer than ``max_token_buffer``
+    code points raises IndexError, the reference's ArrayIndexOutOfBoundsException on its fixed token buffer
+    (``max_doc_buf_size``, SimpleTokenizerLarge.java:59; SimpleTokenizerLargeTest.java:48-75).  (The reference indexes
+    ``Character.codePointAt`` with a code-point counter, SimpleTokenizerLarge.java:66-68, so it misreads text
+    beyond the Basic Multilingual Plane; that quirk is not reproduced.)"""
+    import unicodedata
+    stop = stop if stop is not None else set()
+    out: List[str] = []
+    buf: List[str] = []
+    for ch in text:
+        cat = unicodedata.category(ch)
+        if cat in _WORD or (keep_numbers and cat == "Nd") or (keep_connectors and cat == "Pc"):
+            if len(buf) >= max_token_buffer:
+                raise IndexError(f"token longer than the token buffer ({max_token_buffer})")
+            buf.append(ch)
+        elif cat in _DELIM:
+            if buf:
+                tok = "".join(buf)
+                if tok not in stop:
+                    out.append(tok)
+                buf = []
+    if buf:
+        tok = "".join(buf)
+        if tok not in stop:
+            out.append(tok)
+    return out
+
+
+def _read_stoplist(stoplist) -> set:
+    """A stop list file holds one word per line (MALLET SimpleTokenizer(File)); an iterable is taken as is."""
+    if stoplist is None:
+        return set()
+    if isinstance(stoplist, str):
+        with open(stoplist, "r", encoding="utf-8") as f:
+            return {ln.strip() for ln in f if ln.strip()}
+    return set(stoplist)
+
+
+def _read_lines(path: str):
+    """(name, label, lower-cased text) per line, CsvIterator with LDAUtils.java:236's regex + CharSequenceLowercase."""
     with open(path, "r", encoding="utf-8") as f:
         for line in f:
             line = line.rstrip("\n")
@@ -120,15 +166,72 @@ def load_dataset(path: str, stoplist: Optional[Iterable[str]] = None, keep_numbe
             m = _LINE.match(line)
             if not m:
                 continue
-            name, label, text = m.group(1), m.group(2).strip(), m.group(3)
-            ids = []
-            for tok in _TOKEN.findall(text.lower()):
-                if tok in stop or (not keep_numbers and tok.isdigit()):
-                    continue
-                ids.append(il.alphabet.lookupIndex(tok))
-            il.docs.append(np.asarray(ids, np.int32))
-            il.names.append(name)
-            il.labels.append(label)
+            yield m.group(1), m.group(2).strip(), m.group(3).lower()
+
+
+def corpus_statistics(path: str, stop: set, keep_numbers: bool, keep_connectors: bool, alphabet: Alphabet,
+                      max_token_buffer: int = 10000):
+    """First pass of loadInstancesPrune / loadInstancesKeep: per word id its corpus count (tf,
+    TfIdfPipe.getTf) and the number of documents containing it (df, TfIdfPipe.getIdf); returns (tf, df, D)."""
+    tf: dict = {}
+    df: dict = {}
+    n_docs = 0
+    for _, _, text in _read_lines(path):
+        seen = set()
+        for tok in tokenize(text, stop, keep_numbers, keep_connectors, max_token_buffer):
+            i = alphabet.lookupIndex(tok)
+            tf[i] = tf.get(i, 0) + 1
+            if i not in seen:
+                seen.add(i)
+                df[i] = df.get(i, 0) + 1
+        n_docs += 1
+    return tf, df, n_docs
+
+
+def tfidf_ranking(tf: dict, df: dict, n_docs: int, n_types: int) -> List[int]:
+    """Word ids by ``tf * ln(D / df)`` descending (pipe/TfIdfPipe.java:75-104); ties: higher id first, MALLET's
+    IDSorter order, which is what TfIdfPipeTest.java:118-137 expects ("a" 3, "is" 4, "this" 5)."""
+    import math
+    score = [(tf.get(i, 0) * math.log(n_docs / df[i]) if tf.get(i, 0) and df.get(i, 0) else 0.0) for i in range(n_types)]
+    return sorted(range(n_types), key=lambda i: (-score[i], -i))
+
+
+def load_dataset(path: str, stoplist=None, keep_numbers: bool = True, alphabet: Optional[Alphabet] = None,
+                 rare_threshold: int = 0, keep_connectors: bool = False, tfidf_vocab_size: int = -1,
+                 max_token_buffer: int = 10000) -> InstanceList:
+    """``LDAUtils.loadDataset`` for a ``name<TAB>label<TAB>text`` file (util/LDAUtils.java:136-182):
+
+    * ``tfidf_vocab_size > 0``: ``loadInstancesKeep`` (util/LDAUtils.java:353-460) -- a first pass counts, per
+      word, its occurrences (tf) and the documents containing it (df); words are ranked by
+      ``tf * ln(D / df)`` descending (pipe/TfIdfPipe.java:75-104) and everything from rank
+      ``tfidf_vocab_size`` on joins the stop list (TfIdfPipe.java:162-172);
+    * otherwise ``loadInstancesPrune`` (util/LDAUtils.java:233-330): with ``rare_threshold > 0`` a first pass
+      counts the words and those seen fewer than ``rare_threshold`` times join the stop list (MALLET
+      FeatureCountPipe.addPrunedWordsToStoplist; its source is not in the reference tree: restated from the
+      2.0.8 release);
+    * second pass: lower-case, tokenise, drop stop words, first-seen vocabulary order
+      (StringList2FeatureSequence).  With a caller-supplied ``alphabet`` both passes share it, as in the
+      reference, so pruned words keep their ids.
+
+    Ties of the TF-IDF ranking follow MALLET's IDSorter (higher id first; restated from memory of 2.0.8)."""
+    stop = _read_stoplist(stoplist)
+    if tfidf_vocab_size > 0 or rare_threshold > 0:
+        first = alphabet if alphabet is not None else Alphabet()
+        tf, df, n_docs = corpus_statistics(path, stop, keep_numbers, keep_connectors, first, max_token_buffer)
+        stop = set(stop)
+        if tfidf_vocab_size > 0:
+            for i in tfidf_ranking(tf, df, n_docs, first.size())[tfidf_vocab_size:]:
+                stop.add(first.lookupObject(i))
+        else:
+            for i in range(first.size()):
+                if tf.get(i, 0) < rare_threshold:
+                    stop.add(first.lookupObject(i))
+    il = InstanceList(alphabet=alphabet if alphabet is not None else Alphabet())
+    for name, label, text in _read_lines(path):
+        ids = [il.alphabet.lookupIndex(tok) for tok in tokenize(text, stop, keep_numbers, keep_connectors, max_token_buffer)]
+        il.docs.append(np.asarray(ids, np.int32))
+        il.names.append(name)
+        il.labels.append(label)
     return il
 
 

@@ -45,6 +45,12 @@ class LDAConfiguration:
     phi_mean_thin: int = 1
     exec_time: float = 10.0               # seconds of cumulative sampling time (LDAConfiguration.java:35)
     dataset: Optional[str] = None
+    stoplist: Optional[str] = None        # file with one stop word per line (ParsedLDAConfiguration.java:298-304)
+    rare_threshold: int = 0               # RARE_WORD_THRESHOLD (LDAConfiguration.java:16)
+    keep_numbers: bool = False            # ParsedLDAConfiguration.java:307-310
+    keep_connecting_punctuation: bool = False   # KEEP_CONNECTING_PUNCTUATION (LDAConfiguration.java:40)
+    tfidf_vocab_size: int = -1            # TF_IDF_VOCAB_SIZE_DEFAULT (LDAConfiguration.java:37)
+    max_doc_buf_size: int = 10000         # token buffer of the tokenizers (ParsedLDAConfiguration.java:402-404)
     gpu_device: int = 0                   # new key
 
     def getNoTopics(self, default: int = 10) -> int:
@@ -64,6 +70,21 @@ class LDAConfiguration:
 
     def getScheme(self) -> str:
         return self.scheme
+
+    def loadDataset(self, dataset_fn: Optional[str] = None, alphabet=None, stoplist_dir: Optional[str] = None):
+        """``LDAUtils.loadDataset(config, dataset_fn[, alphabet])`` (util/LDAUtils.java:136-182) with this
+        configuration's ingest keys.  A relative stop-list name is looked up beside the data set (or in
+        ``stoplist_dir``); a missing or empty file means no stop words."""
+        from .corpus import load_dataset
+        fn = dataset_fn or self.dataset
+        stop = None
+        if self.stoplist:
+            cand = self.stoplist if os.path.isabs(self.stoplist) else os.path.join(
+                stoplist_dir or os.path.dirname(os.path.abspath(fn)), self.stoplist)
+            stop = cand if os.path.exists(cand) else None
+        return load_dataset(fn, stoplist=stop, keep_numbers=self.keep_numbers, alphabet=alphabet,
+                            rare_threshold=self.rare_threshold, keep_connectors=self.keep_connecting_punctuation,
+                            tfidf_vocab_size=self.tfidf_vocab_size, max_token_buffer=self.max_doc_buf_size)
 
     @staticmethod
     def from_cfg(path: str, subconfig: Optional[str] = None, **overrides) -> "LDAConfiguration":
@@ -88,7 +109,9 @@ class LDAConfiguration:
                           ("iterations", int), ("seed", int), ("start_diagnostic", int),
                           ("compute_likelihood", boolean), ("topic_interval", int),
                           ("save_phi_mean", boolean), ("phi_mean_burnin", int), ("phi_mean_thin", int),
-                          ("exec_time", float), ("dataset", str), ("gpu_device", int)):
+                          ("exec_time", float), ("dataset", str), ("stoplist", str), ("rare_threshold", int),
+                          ("keep_numbers", boolean), ("keep_connecting_punctuation", boolean),
+                          ("tfidf_vocab_size", int), ("max_doc_buf_size", int), ("gpu_device", int)):
             if key in vals:
                 setattr(c, key, conv(vals[key].strip()))
         return c

@@ -111,6 +111,57 @@ def test_instance_list_and_loader(tmp_path):
     assert back.size() == 3 and back.getNumTypes() == 5 and back.docs[2].tolist() == [2, 3, 4, 1]
 
 
+def test_tokenizer_classes():
+    """The four tokenizer classes LDAUtils.initTokenizer chooses from (util/LDAUtils.java:532-561)."""
+    text = "ab1c foo_bar x\ty 12 z-w (q) \u00e9t\u00e9"
+    # SimpleTokenizerLarge: digits, TAB and symbols are skipped without ending the token (:113-118)
+    assert L.tokenize(text, keep_numbers=False) == ["abc", "foo", "bar", "xy", "z", "w", "q", "\u00e9t\u00e9"]
+    # NumericAlsoTokenizer: digits build tokens
+    assert L.tokenize(text, keep_numbers=True) == ["ab1c", "foo", "bar", "xy", "12", "z", "w", "q", "\u00e9t\u00e9"]
+    # KeepConnectorPunctuation*: "_" (category Pc) joins (SimpleTokenizerLargeTest.java:77-97 'but_i_can')
+    assert L.tokenize("yes but_i_can", keep_numbers=False, keep_connectors=True) == ["yes", "but_i_can"]
+    assert "but_i_can" not in L.tokenize("yes but_i_can", keep_numbers=False)
+    assert L.tokenize("the cat", stop={"the"}) == ["cat"]
+    # fixed token buffer: ArrayIndexOutOfBoundsException in the reference (SimpleTokenizerLargeTest.java:48-75)
+    with pytest.raises(IndexError):
+        L.tokenize("abcdefghijk", max_token_buffer=10)
+    assert L.tokenize("abcdefghij", max_token_buffer=10) == ["abcdefghij"]
+
+
+def test_tfidf_and_rare_word_pruning(tmp_path):
+    """Expected values of the reference's own test, pipe/TfIdfPipeTest.java:44-137, on its two-line corpus."""
+    p = tmp_path / "tfidf.txt"
+    p.write_text("docno:1\tX\tthis is a sample \ndocno:2\tX\tthis is a another another example example example\n")
+    al = L.Alphabet()
+    tf, df, n = L.corpus_statistics(str(p), set(), True, False, al)
+    word = {al.lookupObject(i): i for i in range(al.size())}
+    assert n == 2
+    assert {w: tf[i] for w, i in word.items()} == {"this": 2, "is": 2, "a": 2, "sample": 1, "another": 2, "example": 3}
+    assert {w: df[i] for w, i in word.items()} == {"this": 2, "is": 2, "a": 2, "sample": 1, "another": 1, "example": 1}
+    ranks = L.tfidf_ranking(tf, df, n, al.size())
+    assert {w: ranks.index(i) for w, i in word.items()} == \
+        {"this": 5, "is": 4, "a": 3, "sample": 2, "another": 1, "example": 0}
+    # loadInstancesKeep: everything from rank 3 on is stopped (TfIdfPipe.java:162-172)
+    kept = L.load_dataset(str(p), tfidf_vocab_size=3)
+    assert [kept.alphabet.lookupObject(i) for i in range(kept.alphabet.size())] == ["sample", "another", "example"]
+    assert [d.tolist() for d in kept.docs] == [[0], [1, 1, 2, 2, 2]]
+    # loadInstancesPrune: words seen fewer than rare_threshold times are stopped; first-seen order of the rest
+    pruned = L.load_dataset(str(p), rare_threshold=2)
+    assert [pruned.alphabet.lookupObject(i) for i in range(pruned.alphabet.size())] == ["this", "is", "a", "another", "example"]
+    assert sum(len(d) for d in pruned.docs) == 11
+    # a caller-supplied alphabet is shared by both passes: pruned words keep their ids (util/LDAUtils.java:250-255,295-300)
+    shared = L.Alphabet()
+    L.load_dataset(str(p), rare_threshold=2, alphabet=shared)
+    assert shared.size() == 6 and shared.lookupObject(3) == "sample"
+    # the configuration keys that drive it (ParsedLDAConfiguration.java:113,298-310,393,402-410)
+    cfg = tmp_path / "c.cfg"
+    cfg.write_text("scheme = gpu_ggs\nrare_threshold = 2\nkeep_numbers = true\nstoplist = stop.txt\ndataset = %s\n" % p)
+    (tmp_path / "stop.txt").write_text("is\n")
+    c = L.LDAConfiguration.from_cfg(str(cfg))
+    il = c.loadDataset()
+    assert [il.alphabet.lookupObject(i) for i in range(il.alphabet.size())] == ["this", "a", "another", "example"]
+
+
 def test_cats_fixture_shape(cats):
     off, tokens = cats
     assert (len(off) - 1, int(tokens.max()) + 1, len(tokens)) == (23, 303, 7788)     # SURVEY section 6
