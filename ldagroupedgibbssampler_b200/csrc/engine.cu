@@ -613,7 +613,7 @@ double lgamma_stirling_host(double z)
 // =============================================================================================
 extern "C" {
 
-const char *ldagpu_version(void) { return "libldagpu 0.2 (sm_100a; GGS + PCGS dense z-step)"; }
+const char *ldagpu_version(void) { return "libldagpu 0.3 (sm_100a; GGS, PCGS, sparse PCGS; peer-memory exchange)"; }
 
 const char *ldagpu_last_error(ldagpu_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 

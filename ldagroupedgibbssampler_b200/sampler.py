@@ -51,6 +51,8 @@ class LDAConfiguration:
     keep_connecting_punctuation: bool = False   # KEEP_CONNECTING_PUNCTUATION (LDAConfiguration.java:40)
     tfidf_vocab_size: int = -1            # TF_IDF_VOCAB_SIZE_DEFAULT (LDAConfiguration.java:37)
     max_doc_buf_size: int = 10000         # token buffer of the tokenizers (ParsedLDAConfiguration.java:402-404)
+    logging_path: Optional[str] = None    # run directory of the reference's LoggingUtils (util/LoggingUtils.java:43-109):
+                                          # log-likelihood.txt / log-posterior.txt are appended there when set
     gpu_device: int = 0                   # new key
 
     def getNoTopics(self, default: int = 10) -> int:
@@ -111,7 +113,8 @@ class LDAConfiguration:
                           ("save_phi_mean", boolean), ("phi_mean_burnin", int), ("phi_mean_thin", int),
                           ("exec_time", float), ("dataset", str), ("stoplist", str), ("rare_threshold", int),
                           ("keep_numbers", boolean), ("keep_connecting_punctuation", boolean),
-                          ("tfidf_vocab_size", int), ("max_doc_buf_size", int), ("gpu_device", int)):
+                          ("tfidf_vocab_size", int), ("max_doc_buf_size", int), ("logging_path", str),
+                          ("gpu_device", int)):
             if key in vals:
                 setattr(c, key, conv(vals[key].strip()))
         return c
@@ -238,6 +241,10 @@ class GpuLDASampler:
         done_total = 0
         while done_total < iterations and not self.getAbort():
             n = min(step, iterations - done_total)
+            if cfg.start_diagnostic > 0:
+                # the diagnostic block runs after every sweep from start_diagnostic on (UPL:707-823)
+                it = self.getCurrentIteration()
+                n = 1 if it + 1 >= cfg.start_diagnostic else min(n, cfg.start_diagnostic - 1 - it)
             if hooked:
                 for _ in range(n):
                     self._one_hooked_sweep()
@@ -247,8 +254,11 @@ class GpuLDASampler:
                 self._ck(self._L.ldagpu_sweep(self._h, n, C.byref(d)))
                 done = d.value
             done_total += done
+            if cfg.start_diagnostic > 0 and done == n and self.getCurrentIteration() >= cfg.start_diagnostic:
+                self._log_posterior_to_file(self.computeLogPosterior())                       # UPL:820-821
             if cfg.compute_likelihood and done == n and done_total % max(1, cfg.topic_interval) == 0:
                 self.loglikelihood.append(self.modelLogLikelihood())
+                self._log_likelihood_to_file(self.loglikelihood[-1])                          # UPL:846-850
             if done < n:
                 break
             z_ms, c_ms, p_ms, _ = self.getTimers()
@@ -395,11 +405,30 @@ class GpuLDASampler:
         return v.value
 
     def computeLogPosterior(self) -> float:
-        """UPL:1573-1634 (GGS: with the sweep's own theta, UPL:716-720)."""
+        """UPL:1573-1634.  GGS evaluates it with the sweep's own theta (UPL:716-720); the other schemes draw a
+        diagnostic theta ~ Dir(n_d + alpha) first (UPL:710-714, util/LDAUtils.java:1662-1673) -- here with the
+        library's theta kernel (counter = current iteration) instead of MALLET's Dirichlet.nextDistribution."""
         self._need()
+        if self.scheme != "gpu_ggs":
+            self._ck(self._L.ldagpu_sample_theta(self._h))
         v = C.c_double(0)
         self._ck(self._L.ldagpu_log_posterior(self._h, C.byref(v)))
         return v.value
+
+    def _log_posterior_to_file(self, lp: float):
+        """util/LDAUtils.java:955-968: `iteration<TAB>logPosterior (6 decimals)<TAB>millis` appended to log-posterior.txt"""
+        if self.config.logging_path and self._rank == 0:
+            import time
+            os.makedirs(self.config.logging_path, exist_ok=True)
+            with open(os.path.join(self.config.logging_path, "log-posterior.txt"), "a") as f:
+                f.write("%d\t%.6f\t%d\n" % (self.getCurrentIteration(), lp, int(time.time() * 1000)))
+
+    def _log_likelihood_to_file(self, ll: float):
+        """util/LDAUtils.java:971-979: `iteration<TAB>logLik` appended to log-likelihood.txt"""
+        if self.config.logging_path and self._rank == 0:
+            os.makedirs(self.config.logging_path, exist_ok=True)
+            with open(os.path.join(self.config.logging_path, "log-likelihood.txt"), "a") as f:
+                f.write("%d\t%r\n" % (self.getCurrentIteration(), ll))
 
     # hooks (MSL:783-810): no-ops; subclasses override, sample() then runs step-wise
     def preSample(self): pass

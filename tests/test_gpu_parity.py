@@ -152,6 +152,34 @@ def test_whole_sweeps_bit_exact_synthetic(oracle, scheme, osch, K):
         want_lp = oracle.log_posterior(off, tokens, st["z"], K, V, st["theta"].astype(np.float64),
                                        st["phiT"].astype(np.float64), np.full(K, alpha), beta)
         assert abs(s.computeLogPosterior() - want_lp) <= 1e-9 * abs(want_lp)
+    else:
+        # PCGS diagnostics draw theta ~ Dir(n_d + alpha) from the current z first (UPL:710-714)
+        th = oracle.theta_contract(off, st["z"], K, np.full(K, alpha), seed, s.getCurrentIteration())
+        want_lp = oracle.log_posterior(off, tokens, st["z"], K, V, th.astype(np.float64),
+                                       st["phiT"].astype(np.float64), np.full(K, alpha), beta)
+        assert abs(s.computeLogPosterior() - want_lp) <= 1e-9 * abs(want_lp)
+        assert np.array_equal(s.getTheta().astype(np.float32), th)
+    s.close()
+
+
+def test_diagnostic_files(oracle, tmp_path):
+    """log-posterior.txt / log-likelihood.txt as the reference's sweep loop appends them
+    (UPL:707-823,838-850; util/LDAUtils.java:955-979)."""
+    import ldagroupedgibbssampler_b200 as L
+    off, tokens = make_corpus(40, 120, 30, seed=5)
+    cfg = L.LDAConfiguration(scheme="gpu_ggs", topics=8, alpha=0.5, beta=0.01, seed=3, exec_time=0,
+                             start_diagnostic=3, compute_likelihood=True, topic_interval=2,
+                             logging_path=str(tmp_path / "run"))
+    s = L.GpuLDASampler(cfg, device=0)
+    s.addInstances(L.InstanceList.from_csr(off, tokens, 120))
+    s.sample(6)
+    lp = [ln.split("\t") for ln in open(tmp_path / "run" / "log-posterior.txt").read().splitlines()]
+    assert [int(r[0]) for r in lp] == [3, 4, 5, 6] and all(len(r) == 3 for r in lp)
+    assert abs(float(lp[-1][1]) - s.computeLogPosterior()) <= 1e-6 * abs(float(lp[-1][1])) + 1e-6
+    ll = [ln.split("\t") for ln in open(tmp_path / "run" / "log-likelihood.txt").read().splitlines()]
+    assert [int(r[0]) for r in ll] == [2, 4, 6]
+    assert float(ll[-1][1]) == s.getLogLikelihood()[-1] == s.modelLogLikelihood()
+    assert len(s.getLogLikelihood()) == 4          # iteration 0 (UPL:587-593) + 2, 4, 6
     s.close()
 
 
