@@ -54,6 +54,7 @@ public class GpuLDASampler extends ModifiedSimpleLDA implements LDAGibbsSampler,
     private static final MethodHandle LOG_LIKELIHOOD = fn("ldagpu_log_likelihood", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
     private static final MethodHandle LOG_POSTERIOR = fn("ldagpu_log_posterior", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
     private static final MethodHandle ABORT = fn("ldagpu_abort", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    private static final MethodHandle SAMPLE_THETA = fn("ldagpu_sample_theta", FunctionDescriptor.of(JAVA_INT, ADDRESS));
 
     private final Arena arena = Arena.ofShared();
     private MemorySegment handle = MemorySegment.NULL;
@@ -253,6 +254,9 @@ public class GpuLDASampler extends ModifiedSimpleLDA implements LDAGibbsSampler,
     /** replaces the `whichModel.equals("ggs")` test of UPL:710: the GPU sampler owns its diagnostic theta */
     public double computeLogPosterior() {
         try (Arena a = Arena.ofConfined()) {
+            // PCGS / sparse PCGS: diagnostic theta ~ Dir(n_d + alpha) from the current z first (UPL:710-714,
+            // util/LDAUtils.java:1662-1673); GGS keeps the sweep's own theta (UPL:716-720)
+            if (scheme != 0) ck((int) SAMPLE_THETA.invokeExact(handle));
             MemorySegment v = a.allocate(JAVA_DOUBLE);
             ck((int) LOG_POSTERIOR.invokeExact(handle, v));
             return v.get(JAVA_DOUBLE, 0);
