@@ -14,7 +14,8 @@ Default workload: PubMed-shaped GGS, K=1000, V=141043, one eighth of the 8.2M-do
 value   device-resident: K sweeps inside ONE ldagpu_sweep call, timed with CUDA events on the library's
         stream, max over ranks.
 e2e     the same metric through the sampler API with host buffers: every step uploads z from pinned
-        host memory (setZIndicators path, keeps Phi), runs sample(1), reads z and the topic totals back.
+        host memory (setZIndicators path, keeps Phi), runs sample(1, z_out=...) which reads z back, and
+        reads the topic totals.
 """
 from __future__ import annotations
 
@@ -297,8 +298,7 @@ def main():
 
     def e2e_step():
         s._ck(lib.ldagpu_set_z(s._h, C.c_void_p(zbuf.data_ptr()), 0))        # H2D z (+ count rebuild, Phi kept)
-        s.sample(1)
-        s._ck(lib.ldagpu_get_z(s._h, C.c_void_p(zbuf.data_ptr())))           # D2H z
+        s.sample(1, z_out=znp)                                              # sweep; D2H z under the Phi draw
         return s.getTopicTotals()                                           # D2H n_k
 
     for _ in range(max(1, min(args.warmup, 2))):
@@ -345,8 +345,9 @@ def main():
            "clocks": ck,
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n_local,
                    "d2h_bytes_per_step": 4 * n_local + 4 * wl["K"], "ms_per_step": e2e_ms / args.steps,
-                   "what": "per step: ldagpu_set_z from pinned host z, sample(1), ldagpu_get_z to pinned host, "
-                           "getTopicTotals; host wall clock, max over ranks"},
+                   "what": "per step: ldagpu_set_z from pinned host z (upload pipelined with the count rebuild), "
+                           "sample(1, z_out=pinned host z) (z read back while the Phi draw runs), getTopicTotals; "
+                           "host wall clock, max over ranks"},
            "gpu_launches": int(launches),
            "roofline": roofline,
            "timers_ms": dict(zip(("z", "counts", "phi", "comm"), s.getTimers()))}

@@ -87,6 +87,11 @@ int ldagpu_get_z(ldagpu_handle h, int32_t *z);
 /* sample(iterations) (LGS:15, UPL:552-943): n full sweeps = [theta] z, counts, Phi.
  * Stops early when ldagpu_abort was called (UPL:645,906-910); *done receives the sweeps run. */
 int ldagpu_sweep(ldagpu_handle h, int32_t n, int32_t *done);
+/* sample(iterations) followed by getZIndicators in one call: the indicators of the last sweep travel to the host
+ * buffer z (int32[N], pinned memory for the overlap) while that sweep's count exchange and Phi draw still run.
+ * This is what the Java shim's sample() does: z goes back into the documents' LabelSequences after every call
+ * (MSL:464-477, util/LDAUtils.java:1552-1571 read it from there). */
+int ldagpu_sweep_get_z(ldagpu_handle h, int32_t n, int32_t *done, int32_t *z);
 /* sampleZGivenPhi(iterations) (LSWP:11, UPL:975-1014): z and counts only, Phi frozen */
 int ldagpu_sample_z_given_phi(ldagpu_handle h, int32_t n, int32_t *done);
 /* step-wise entry points (tests, and hosts that interleave their own hooks preZ/postZ/prePhi/postPhi,

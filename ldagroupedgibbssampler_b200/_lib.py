@@ -14,7 +14,7 @@ SO_PATH = os.environ.get("LDAGPU_LIBRARY") or os.path.join(_HERE, "libldagpu.so"
 SYMBOLS = [
     "ldagpu_version", "ldagpu_last_error", "ldagpu_device_count", "ldagpu_create", "ldagpu_destroy",
     "ldagpu_comm_unique_id", "ldagpu_comm_init", "ldagpu_get_exchange_mode", "ldagpu_init_z_java_random", "ldagpu_set_z",
-    "ldagpu_get_z", "ldagpu_sweep", "ldagpu_sample_z_given_phi", "ldagpu_next_iteration",
+    "ldagpu_get_z", "ldagpu_sweep", "ldagpu_sweep_get_z", "ldagpu_sample_z_given_phi", "ldagpu_next_iteration",
     "ldagpu_sample_theta", "ldagpu_sample_z", "ldagpu_rebuild_counts", "ldagpu_sample_phi",
     "ldagpu_get_iteration", "ldagpu_set_iteration", "ldagpu_get_type_topic_counts",
     "ldagpu_get_topic_totals", "ldagpu_get_doc_topic_counts", "ldagpu_get_phi", "ldagpu_set_phi",
@@ -60,6 +60,7 @@ def load() -> C.CDLL:
     sig("ldagpu_set_z", C.c_int, vp, vp, i32)
     sig("ldagpu_get_z", C.c_int, vp, vp)
     sig("ldagpu_sweep", C.c_int, vp, i32, pi32)
+    sig("ldagpu_sweep_get_z", C.c_int, vp, i32, pi32, vp)
     sig("ldagpu_sample_z_given_phi", C.c_int, vp, i32, pi32)
     for n in ("ldagpu_next_iteration", "ldagpu_sample_theta", "ldagpu_sample_z", "ldagpu_rebuild_counts",
               "ldagpu_sample_phi", "ldagpu_abort"):

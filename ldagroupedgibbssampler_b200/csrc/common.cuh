@@ -118,6 +118,8 @@ cudaError_t launch_z_spalias(const ZArgs &z, const AliasSlot *table, const float
 inline int max_dense_topics(bool pcgs) { return pcgs ? 18000 : 27000; }
 cudaError_t launch_counts(const Dims &dm, const int32_t *tokens, const int32_t *z, int32_t *n_wk,
                           int32_t *n_k, int sm_count, cudaStream_t st);
+cudaError_t launch_counts_chunk(const Dims &dm, const int32_t *tokens, const int32_t *z, int64_t n, int32_t *n_wk,
+                                int *bad, int sm_count, cudaStream_t st);
 cudaError_t launch_topic_totals(const Dims &dm, const int32_t *n_wk, int32_t *n_k, cudaStream_t st);
 cudaError_t launch_doc_topic_counts(const Dims &dm, const int64_t *doc_off, const int32_t *z,
                                     int32_t *n_dk /*[D][K] dense*/, cudaStream_t st);

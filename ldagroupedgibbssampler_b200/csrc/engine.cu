@@ -148,6 +148,9 @@ struct ldagpu_handle_s {
 
     cudaStream_t stream = nullptr;
     std::vector<cudaEvent_t> events;
+    // host <-> device copies of z overlap the kernels next to them: a second stream and a few ordering events
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> copy_events;
 
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
@@ -391,7 +394,10 @@ int sync_check(ldagpu_handle h)
     return 0;
 }
 
-int run_sweeps(ldagpu_handle h, int32_t n, bool with_phi, int32_t *done)
+// z_out != nullptr: the topic indicators of the last sweep are copied to the host on the copy stream as soon as
+// its z-step has finished, under the count exchange and the Phi draw (the Java shim copies z back into the
+// documents' LabelSequences after every sample() call)
+int run_sweeps(ldagpu_handle h, int32_t n, bool with_phi, int32_t *done, int32_t *z_out = nullptr)
 {
     h->last_zk_ms = 0; h->last_call_ms = 0; h->last_zk_launches = 0; h->last_launches = 0;
     if (done) *done = 0;
@@ -399,6 +405,7 @@ int run_sweeps(ldagpu_handle h, int32_t n, bool with_phi, int32_t *done)
     if (ensure_events(h, (size_t)n * EV_PER_SWEEP)) return 1;
     if (rendezvous(h)) return 1;
     int32_t ran = 0;
+    bool z_copied = false;
     for (int32_t s = 0; s < n; ++s) {
         if (h->abort_flag.load(std::memory_order_relaxed)) break;
         cudaEvent_t *ev = h->events.data() + (size_t)s * EV_PER_SWEEP;
@@ -410,6 +417,12 @@ int run_sweeps(ldagpu_handle h, int32_t n, bool with_phi, int32_t *done)
         CK(h, cudaEventRecord(ev[1], h->stream));
         if (step_z(h, true)) return 1;
         CK(h, cudaEventRecord(ev[2], h->stream));
+        if (z_out && s == n - 1 && h->dm.N) {
+            CK(h, cudaEventRecord(h->copy_events[0], h->stream));
+            CK(h, cudaStreamWaitEvent(h->copy_stream, h->copy_events[0], 0));
+            CK(h, cudaMemcpyAsync(z_out, h->z.p, sizeof(int32_t) * (size_t)h->dm.N, cudaMemcpyDeviceToHost, h->copy_stream));
+            z_copied = true;
+        }
         CK(h, launch_topic_totals(h->dm, h->n_wk.p, h->n_k.p, h->stream));
         h->last_launches += 1;
         CK(h, cudaEventRecord(ev[3], h->stream));
@@ -424,7 +437,10 @@ int run_sweeps(ldagpu_handle h, int32_t n, bool with_phi, int32_t *done)
         }
         ++ran;
     }
+    if (z_out && !z_copied && h->dm.N)   // aborted before the last sweep (or n == 0): plain copy of the current z
+        CK(h, cudaMemcpyAsync(z_out, h->z.p, sizeof(int32_t) * (size_t)h->dm.N, cudaMemcpyDeviceToHost, h->stream));
     if (sync_check(h)) return 1;
+    if (z_copied) CK(h, cudaStreamSynchronize(h->copy_stream));
     for (int32_t s = 0; s < ran; ++s) {
         cudaEvent_t *ev = h->events.data() + (size_t)s * EV_PER_SWEEP;
         float ms[EV_PER_SWEEP - 1];
@@ -485,16 +501,6 @@ int build_items(ldagpu_handle h)
         CK(h, cudaMemcpy(h->item_doc.p, item_doc.data(), sizeof(int32_t) * item_doc.size(), cudaMemcpyHostToDevice));
     if (!item_begin.empty())
         CK(h, cudaMemcpy(h->item_begin.p, item_begin.data(), sizeof(int64_t) * item_begin.size(), cudaMemcpyHostToDevice));
-    return 0;
-}
-
-int validate_z(ldagpu_handle h)
-{
-    CK(h, launch_validate(h->dm, nullptr, h->z.p, h->bad.p, h->stream));
-    int bad = 0;
-    CK(h, cudaMemcpyAsync(&bad, h->bad.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(h, cudaStreamSynchronize(h->stream));
-    if (bad) return h->fail("topic indicator out of range [0, %d)", h->dm.K);   // UPL:475-481 throws
     return 0;
 }
 
@@ -670,6 +676,12 @@ int ldagpu_create(int32_t K, int32_t V, int64_t D, const int64_t *doc_offsets, c
         CK(h, cudaGetDeviceProperties(&prop, device));
         h->sm_count = prop.multiProcessorCount;
         CK(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        CK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 10; ++i) {
+            cudaEvent_t e;
+            CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            h->copy_events.push_back(e);
+        }
         const size_t N1 = (size_t)std::max<int64_t>(dm.N, 1);
         CK(h, h->doc_off.alloc((size_t)D + 1));
         CK(h, h->tokens.alloc(N1 + 4));
@@ -750,6 +762,8 @@ int ldagpu_destroy(ldagpu_handle h)
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     h->nk_parts.release(); h->p2p_flags.release(); h->p2p_local.release();
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->copy_events) cudaEventDestroy(e);
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     h->doc_off.release(); h->item_begin.release(); h->tokens.release(); h->z.release(); h->n_wk.release();
     h->n_k.release(); h->item_doc.release(); h->scratch_i32.release(); h->phiT.release(); h->theta.release();
     h->alpha_f.release(); h->alpha_d.release(); h->lgs_alpha.release(); h->partial.release(); h->seg.release(); h->topic_sum.release();
@@ -834,10 +848,41 @@ int ldagpu_init_z_java_random(ldagpu_handle h, int32_t seed)
 int ldagpu_set_z(ldagpu_handle h, const int32_t *z, int32_t redraw_phi)
 {
     NEED(h);
+    const int64_t N = h->dm.N;
+    if (!z && N) return h->fail("null z");
+    // upload and count rebuild pipelined chunk by chunk: the copy stream brings z in, the main stream checks
+    // the range and accumulates n_wk for the chunk that has landed (UPL:1797-1830 rebuilds while it copies too)
+    CK(h, cudaMemsetAsync(h->n_wk.p, 0, sizeof(int32_t) * h->n_wk.n, h->stream));
+    CK(h, cudaMemsetAsync(h->bad.p, 0, sizeof(int), h->stream));
+    CK(h, cudaEventRecord(h->copy_events[0], h->stream));
+    CK(h, cudaStreamWaitEvent(h->copy_stream, h->copy_events[0], 0));   // earlier readers of z are done
+    const int nchunk = N >= (8 << 20) ? 8 : 1;
+    const int64_t per = ((N + nchunk - 1) / nchunk + 3) / 4 * 4;        // int4 loads: chunks start on 16-byte boundaries
+    for (int c = 0; c < nchunk; ++c) {
+        const int64_t o = (int64_t)c * per, cnt = std::min<int64_t>(per, N - o);
+        if (cnt <= 0) break;
+        CK(h, cudaMemcpyAsync(h->z.p + o, z + o, sizeof(int32_t) * (size_t)cnt, cudaMemcpyHostToDevice, h->copy_stream));
+        CK(h, cudaEventRecord(h->copy_events[1 + c], h->copy_stream));
+        CK(h, cudaStreamWaitEvent(h->stream, h->copy_events[1 + c], 0));
+        CK(h, launch_counts_chunk(h->dm, h->tokens.p + o, h->z.p + o, cnt, h->n_wk.p, h->bad.p, h->sm_count, h->stream));
+    }
+    CK(h, launch_topic_totals(h->dm, h->n_wk.p, h->n_k.p, h->stream));
+    h->last_launches += nchunk + 1;
+    int bad = 0;
+    CK(h, cudaMemcpyAsync(&bad, h->bad.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (bad) return h->fail("topic indicator out of range [0, %d)", h->dm.K);   // UPL:475-481 throws
+    if (rendezvous(h)) return 1;
+    if (step_counts_exchange(h, redraw_phi != 0)) return 1;
+    if (redraw_phi && step_phi(h, false, nullptr, true)) return 1;   // UPL:1842
+    return sync_check(h);
+}
+
+int ldagpu_sweep_get_z(ldagpu_handle h, int32_t n, int32_t *done, int32_t *z)
+{
+    NEED(h);
     if (!z && h->dm.N) return h->fail("null z");
-    if (h->dm.N) CK(h, cudaMemcpyAsync(h->z.p, z, sizeof(int32_t) * (size_t)h->dm.N, cudaMemcpyHostToDevice, h->stream));
-    if (validate_z(h)) return 1;
-    return refresh_counts_and_phi(h, redraw_phi != 0);   // UPL:1842
+    return run_sweeps(h, n, true, done, z);
 }
 
 int ldagpu_get_z(ldagpu_handle h, int32_t *z)

@@ -24,9 +24,12 @@ constexpr unsigned FULL = 0xffffffffu;
 // ---------------------------------------------------------------------------------------
 constexpr int CNT_THREADS = 256;
 
+// CHECK: z comes straight from the host (setZIndicators): an indicator outside [0, K) raises the error
+// word and is skipped instead of being counted (UncollapsedParallelLDA.java:475-481 throws)
+template <bool CHECK>
 __global__ void __launch_bounds__(CNT_THREADS)
 counts_kernel(Dims dm, const int32_t *__restrict__ tokens, const int32_t *__restrict__ z,
-              int32_t *__restrict__ n_wk)
+              int32_t *__restrict__ n_wk, int *__restrict__ bad)
 {
     const int64_t n4 = dm.N / 4;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -39,6 +42,11 @@ counts_kernel(Dims dm, const int32_t *__restrict__ tokens, const int32_t *__rest
         const int zz[4] = {z4.x, z4.y, z4.z, z4.w};
 #pragma unroll
         for (int s = 0; s < 4; ++s) key[s] = (size_t)ww[s] * (size_t)dm.Ks + (size_t)zz[s];
+        if (CHECK) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                if ((unsigned)zz[s] >= (unsigned)dm.K) { c[s] = 0; key[s] = ~(size_t)0 - (size_t)s; atomicOr(bad, 2); }
+        }
 #pragma unroll
         for (int s = 3; s > 0; --s)
             if (key[s] == key[s - 1]) { c[s - 1] += c[s]; c[s] = 0; }
@@ -48,8 +56,26 @@ counts_kernel(Dims dm, const int32_t *__restrict__ tokens, const int32_t *__rest
     }
     // scalar tail (N % 4 tokens), done by block 0
     if (blockIdx.x == 0)
-        for (int64_t i = n4 * 4 + threadIdx.x; i < dm.N; i += blockDim.x)
+        for (int64_t i = n4 * 4 + threadIdx.x; i < dm.N; i += blockDim.x) {
+            if (CHECK && (unsigned)z[i] >= (unsigned)dm.K) { atomicOr(bad, 2); continue; }
             atomicAdd(&n_wk[(size_t)tokens[i] * dm.Ks + z[i]], 1);
+        }
+}
+
+// counts of tokens [0, n) of the given (offset) arrays added into n_wk, with the range check; no reset, no
+// totals: ldagpu_set_z pipelines the host-to-device copy of z with this kernel chunk by chunk
+cudaError_t launch_counts_chunk(const Dims &dm, const int32_t *tokens, const int32_t *z, int64_t n, int32_t *n_wk,
+                                int *bad, int sm_count, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    Dims d = dm;
+    d.N = n;
+    int64_t need = (n / 4 + CNT_THREADS - 1) / CNT_THREADS;
+    int64_t grid = (int64_t)sm_count * 8;
+    if (need < grid) grid = need;
+    if (grid < 1) grid = 1;
+    counts_kernel<true><<<(unsigned)grid, CNT_THREADS, 0, st>>>(d, tokens, z, n_wk, bad);
+    return cudaGetLastError();
 }
 
 // n_k = column sums of n_wk.  (A shared-memory histogram of z inside counts_kernel serialised on the
@@ -89,7 +115,7 @@ cudaError_t launch_counts(const Dims &dm, const int32_t *tokens, const int32_t *
         int64_t grid = (int64_t)sm_count * 8;
         if (need < grid) grid = need;
         if (grid < 1) grid = 1;
-        counts_kernel<<<(unsigned)grid, CNT_THREADS, 0, st>>>(dm, tokens, z, n_wk);
+        counts_kernel<false><<<(unsigned)grid, CNT_THREADS, 0, st>>>(dm, tokens, z, n_wk, nullptr);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

@@ -224,11 +224,16 @@ class GpuLDASampler:
     def addTestInstances(self, testSet: InstanceList):
         raise NotImplementedError("held-out evaluation (MarginalProbEstimatorPlain) is outside the GPU path")
 
-    def sample(self, iterations: int):
+    def sample(self, iterations: int, z_out: Optional[np.ndarray] = None):
         """UPL:552-943: `iterations` sweeps; log-likelihood every topic_interval sweeps when
-        compute_likelihood is set (UPL:587-593,838-853)."""
+        compute_likelihood is set (UPL:587-593,838-853).  ``z_out`` (int32[N], ideally pinned): receives the
+        topic indicators after the last sweep, copied while that sweep's Phi draw still runs
+        (``ldagpu_sweep_get_z``) -- what the Java shim does after every sample() call."""
         self._need()
         cfg = self.config
+        z_filled = False
+        if z_out is not None and (z_out.dtype != np.int32 or not z_out.flags.c_contiguous or z_out.size < len(self._tokens)):
+            raise ValueError("z_out must be a contiguous int32 array of at least N elements")
         if cfg.save_phi_mean:
             burn = int(cfg.phi_mean_burnin / 100.0 * iterations)          # UPL:206-207
             self._ck(self._L.ldagpu_set_phi_mean_schedule(self._h, burn, cfg.phi_mean_thin))
@@ -251,7 +256,11 @@ class GpuLDASampler:
                 done = n
             else:
                 d = C.c_int32(0)
-                self._ck(self._L.ldagpu_sweep(self._h, n, C.byref(d)))
+                if z_out is not None and done_total + n >= iterations:
+                    self._ck(self._L.ldagpu_sweep_get_z(self._h, n, C.byref(d), ptr(z_out)))
+                    z_filled = True
+                else:
+                    self._ck(self._L.ldagpu_sweep(self._h, n, C.byref(d)))
                 done = d.value
             done_total += done
             if cfg.start_diagnostic > 0 and done == n and self.getCurrentIteration() >= cfg.start_diagnostic:
@@ -264,6 +273,8 @@ class GpuLDASampler:
             z_ms, c_ms, p_ms, _ = self.getTimers()
             if (z_ms + c_ms + p_ms) / 1000.0 >= cfg.exec_time > 0:        # UPL:926-928
                 break
+        if z_out is not None and not z_filled:
+            self._ck(self._L.ldagpu_get_z(self._h, ptr(z_out)))
         self.postSample()
 
     def _one_hooked_sweep(self):

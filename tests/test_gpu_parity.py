@@ -162,6 +162,33 @@ def test_whole_sweeps_bit_exact_synthetic(oracle, scheme, osch, K):
     s.close()
 
 
+def test_sample_with_z_read_back_and_pipelined_set_z(oracle):
+    """ldagpu_sweep_get_z: z of the last sweep arrives in the host buffer; ldagpu_set_z uploads in chunks with
+    the range check inside the count kernel."""
+    off, tokens = make_corpus(3000, 500, 60, seed=21)        # > 8 Mi tokens is not needed: one chunk here
+    K, V, alpha, beta = 64, 500, 0.2, 0.01
+    a = _sampler("gpu_ggs", off, tokens, V, K, alpha, beta, 5)
+    b = _sampler("gpu_ggs", off, tokens, V, K, alpha, beta, 5)
+    zbuf = np.full(len(tokens), -1, np.int32)
+    a.sample(3, z_out=zbuf)
+    b.sample(3)
+    assert np.array_equal(zbuf, a.get_z_flat()) and np.array_equal(zbuf, b.get_z_flat())
+    assert np.array_equal(a.getTypeTopicMatrix(), b.getTypeTopicMatrix())
+    zbuf2 = np.zeros(len(tokens), np.int32)
+    a.sample(0, z_out=zbuf2)                                  # no sweep: plain copy of the current z
+    assert np.array_equal(zbuf2, zbuf)
+    # set_z: counts follow the uploaded z; an out-of-range indicator is reported, not counted
+    n_wk, n_k = oracle.rebuild_counts(tokens, zbuf, V, K)
+    b.set_z_flat(zbuf, redraw_phi=False)
+    assert np.array_equal(b.getTypeTopicMatrix(), n_wk) and np.array_equal(b.getTopicTotals(), n_k)
+    bad = zbuf.copy(); bad[len(bad) // 2] = K
+    with pytest.raises(Exception, match="out of range"):
+        b.set_z_flat(bad, redraw_phi=False)
+    with pytest.raises(ValueError):
+        a.sample(1, z_out=np.zeros(3, np.int32))
+    a.close(); b.close()
+
+
 def test_diagnostic_files(oracle, tmp_path):
     """log-posterior.txt / log-likelihood.txt as the reference's sweep loop appends them
     (UPL:707-823,838-850; util/LDAUtils.java:955-979)."""
