@@ -34,7 +34,7 @@ def _newer(src: str, dst: str) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT) -> str:
-    """defines / out: tuning variants, e.g. build(defines=["Z_STAGES=2"], out=".../libldagpu_s2.so")."""
+    """defines / out: tuning variants, e.g. build(defines=["Z_MINB_DEF=3"], out=".../libldagpu_m3.so")."""
     global OBJ
     if defines:
         OBJ = os.path.join(HERE, "_obj_" + "_".join(d.replace("=", "") for d in defines))

@@ -868,10 +868,13 @@ int ldagpu_set_z(ldagpu_handle h, const int32_t *z, int32_t redraw_phi)
     }
     CK(h, launch_topic_totals(h->dm, h->n_wk.p, h->n_k.p, h->stream));
     h->last_launches += nchunk + 1;
+    // sharded: every rank must take the same exit, or the others would wait for this one in the exchange
+    if (h->world > 1) NK(h, g_nccl.AllReduce(h->bad.p, h->bad.p, 1, ncclInt32, ncclMax, h->comm, h->stream));
     int bad = 0;
     CK(h, cudaMemcpyAsync(&bad, h->bad.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
-    if (bad) return h->fail("topic indicator out of range [0, %d)", h->dm.K);   // UPL:475-481 throws
+    if (bad) return h->fail("topic indicator out of range [0, %d)%s", h->dm.K,   // UPL:475-481 throws
+                            h->world > 1 ? " (on this or another rank)" : "");
     if (rendezvous(h)) return 1;
     if (step_counts_exchange(h, redraw_phi != 0)) return 1;
     if (redraw_phi && step_phi(h, false, nullptr, true)) return 1;   // UPL:1842

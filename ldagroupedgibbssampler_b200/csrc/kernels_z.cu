@@ -5,12 +5,13 @@
 //   UncollapsedParallelLDA.java:1466-1545   PCGS z-step
 //   UncollapsedParallelLDA.java:1354-1437   RecursiveDocumentSampler / loopOverBatches (scheduling)
 //
-// Design: one warp owns one work item (GGS: a chunk of <= 256 tokens of one
+// Design: one warp owns one work item (GGS: a chunk of 32..256 tokens of one
 // document; PCGS: one whole document, because n_dk changes token by token).  The K topics of a
 // token are spread over the lanes, lane l owning topics 4l..4l+3 of every 128-topic tile, so one
 // Phi^T row is read as coalesced float4.  Rows are fetched by the TMA engine (cp.async.bulk,
-// 1-D) into a per-warp shared-memory ring, a few rows ahead of the consumer.  A run of equal
-// word types shares one row fetch (and, for GGS, one prefix scan).  The categorical draw is a
+// 1-D) into a per-warp shared-memory slot; the row is copied to registers as soon as it lands and
+// the slot is refilled with the next run's row while the warp computes.  A run of equal
+// word types shares one row fetch (and, for GGS, one set of tile totals).  The categorical draw is a
 // fixed three-level fp32 prefix tree (lane-local fma prefix, distributed-butterfly tile totals,
 // Kogge-Stone scan inside the chosen tile) so the CPU oracle can reproduce the sampled topic bit for bit; uniforms are
 // Philox4x32-10 keyed by the global token index.
@@ -20,10 +21,10 @@
 namespace ldagpu {
 
 constexpr unsigned FULL = 0xffffffffu;
-// Tuning (measured on B200, PubMed-shaped K=1000 / Enron-shaped K=400, profiles/r01_tuning.md): the
-// kernel is bound by shuffle/shared-pipe latency, not by row fetches (83 % of them hit L2), so
-// resident warps matter more than prefetch depth: 1 ring slot and 4 CTAs/SM (32 warps, 64
-// registers, 72 B of spills at K=1000) beat 3 slots and 2 CTAs/SM by 20 %.
+// Tuning (measured on B200, PubMed-shaped K=1000 / Enron-shaped K=400, profiles/README.md): the
+// kernel is bound by the SM's shared-memory data pipe (row copy + shuffles + spill reloads), not by
+// row fetches (80 % of them hit L2), so resident warps matter more than prefetch depth: one slot
+// and 4 CTAs/SM beat three slots and 2 CTAs/SM by 20 %.
 #ifndef Z_MINB_DEF
 #define Z_MINB_DEF 4
 #endif
