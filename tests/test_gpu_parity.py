@@ -189,6 +189,27 @@ def test_sample_with_z_read_back_and_pipelined_set_z(oracle):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("scheme", ["gpu_ggs", "gpu_pcgs", "gpu_spalias"])
+def test_checkpoint_resume_is_exact(oracle, scheme):
+    """State = (z, Phi, iteration): a fresh handle restored from it continues exactly like the original run
+    (all random-number counters are keyed by indices and the iteration, nothing else carries over)."""
+    off, tokens = make_corpus(150, 300, 40, seed=9)
+    K, V, alpha, beta, seed = 96, 300, 0.3, 0.01, 11
+    a = _sampler(scheme, off, tokens, V, K, alpha, beta, seed)
+    a.sample(2)
+    z2, phi2, it2 = a.get_z_flat(), a.getPhi(), a.getCurrentIteration()
+    a.sample(2)
+    b = _sampler(scheme, off, tokens, V, K, alpha, beta, seed)
+    b.set_z_flat(z2, redraw_phi=False)
+    b.setPhi(phi2, None, None)
+    b._L.ldagpu_set_iteration(b._h, it2)
+    b.sample(2)
+    assert np.array_equal(a.get_z_flat(), b.get_z_flat())
+    assert np.array_equal(a.getTypeTopicMatrix(), b.getTypeTopicMatrix())
+    assert np.array_equal(a.getPhi(), b.getPhi())
+    a.close(); b.close()
+
+
 def test_diagnostic_files(oracle, tmp_path):
     """log-posterior.txt / log-likelihood.txt as the reference's sweep loop appends them
     (UPL:707-823,838-850; util/LDAUtils.java:955-979)."""
