@@ -1,0 +1,128 @@
+/*
+ * ldagpu_jni.c -- JNI binding of libldagpu.so for JDK 8-21 (the reference builds with Java 8, pom.xml:152-154).
+ *
+ * java/cc/mallet/topics/GpuLDASampler.java in this repository calls the C ABI through the Panama FFM API
+ * (JDK 22+).  On an older JDK the same class declares the calls as `private static native` methods of a
+ * nested class `cc.mallet.topics.GpuLDASampler$Native` and loads this stub; the C signatures it forwards to
+ * are exactly those of include/ldagpu.h.  NOT compiled in this repository's build image (no JDK, no jni.h).
+ *
+ *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -I../../include \
+ *       ldagpu_jni.c -L<dir of libldagpu.so> -lldagpu -o libldagpu_jni.so
+ *
+ * Java side (excerpt):
+ *   static final class Native {
+ *       static { System.loadLibrary("ldagpu_jni"); }
+ *       static native long   create(int K, int V, long D, long[] docOffsets, int[] tokens, double[] alpha,
+ *                                   double beta, long seed, int scheme, int device, long docBase, long tokenBase);
+ *       static native void   destroy(long h);
+ *       static native void   initZJavaRandom(long h, int seed);
+ *       static native int    sweepGetZ(long h, int n, int[] z);          // returns the sweeps run
+ *       static native void   setZ(long h, int[] z, boolean redrawPhi);
+ *       static native void   getTypeTopicCounts(long h, int[] out);      // int[V*K], row-major [V][K]
+ *       static native void   getTopicTotals(long h, int[] out);
+ *       static native void   getPhi(long h, double[] out);               // double[K*V], row-major [K][V]
+ *       static native double logLikelihood(long h);
+ *       static native double logPosterior(long h);
+ *       static native void   abort(long h);
+ *   }
+ * Every failure is rethrown as IllegalStateException with ldagpu_last_error's message, which is what the
+ * reference's own samplers throw on an invariant break (UncollapsedParallelLDA.java:475-481,1828-1830).
+ */
+#include <jni.h>
+#include <stdint.h>
+
+#include "ldagpu.h"
+
+#define CLS(name) Java_cc_mallet_topics_GpuLDASampler_00024Native_##name
+
+static void throw_last(JNIEnv *env, ldagpu_handle h)
+{
+    jclass ex = (*env)->FindClass(env, "java/lang/IllegalStateException");
+    if (ex) (*env)->ThrowNew(env, ex, ldagpu_last_error(h));
+}
+
+JNIEXPORT jlong JNICALL CLS(create)(JNIEnv *env, jclass c, jint K, jint V, jlong D, jlongArray docOffsets,
+                                    jintArray tokens, jdoubleArray alpha, jdouble beta, jlong seed, jint scheme,
+                                    jint device, jlong docBase, jlong tokenBase)
+{
+    (void)c;
+    ldagpu_handle h = NULL;
+    jlong *off = (*env)->GetLongArrayElements(env, docOffsets, NULL);
+    jint *tok = (*env)->GetIntArrayElements(env, tokens, NULL);
+    jdouble *al = (*env)->GetDoubleArrayElements(env, alpha, NULL);
+    int rc = ldagpu_create(K, V, D, (const int64_t *)off, (const int32_t *)tok, al, beta, (uint64_t)seed, scheme,
+                           device, docBase, tokenBase, &h);
+    (*env)->ReleaseLongArrayElements(env, docOffsets, off, JNI_ABORT);   /* the library has copied everything */
+    (*env)->ReleaseIntArrayElements(env, tokens, tok, JNI_ABORT);
+    (*env)->ReleaseDoubleArrayElements(env, alpha, al, JNI_ABORT);
+    if (rc) { throw_last(env, NULL); return 0; }
+    return (jlong)(intptr_t)h;
+}
+
+JNIEXPORT void JNICALL CLS(destroy)(JNIEnv *env, jclass c, jlong h)
+{
+    (void)env; (void)c;
+    ldagpu_destroy((ldagpu_handle)(intptr_t)h);
+}
+
+JNIEXPORT void JNICALL CLS(initZJavaRandom)(JNIEnv *env, jclass c, jlong h, jint seed)
+{
+    (void)c;
+    if (ldagpu_init_z_java_random((ldagpu_handle)(intptr_t)h, seed)) throw_last(env, (ldagpu_handle)(intptr_t)h);
+}
+
+/* sample(iterations) + the copy of z back into the documents' LabelSequences (one call, copy overlapped) */
+JNIEXPORT jint JNICALL CLS(sweepGetZ)(JNIEnv *env, jclass c, jlong h, jint n, jintArray z)
+{
+    (void)c;
+    int32_t done = 0;
+    jint *zp = (*env)->GetIntArrayElements(env, z, NULL);
+    int rc = ldagpu_sweep_get_z((ldagpu_handle)(intptr_t)h, n, &done, (int32_t *)zp);
+    (*env)->ReleaseIntArrayElements(env, z, zp, rc ? JNI_ABORT : 0);
+    if (rc) throw_last(env, (ldagpu_handle)(intptr_t)h);
+    return done;
+}
+
+JNIEXPORT void JNICALL CLS(setZ)(JNIEnv *env, jclass c, jlong h, jintArray z, jboolean redrawPhi)
+{
+    (void)c;
+    jint *zp = (*env)->GetIntArrayElements(env, z, NULL);
+    int rc = ldagpu_set_z((ldagpu_handle)(intptr_t)h, (const int32_t *)zp, redrawPhi ? 1 : 0);
+    (*env)->ReleaseIntArrayElements(env, z, zp, JNI_ABORT);
+    if (rc) throw_last(env, (ldagpu_handle)(intptr_t)h);
+}
+
+#define GETTER(jname, cfn, jarr, jelem, ctype, Get, Release)                                    \
+    JNIEXPORT void JNICALL CLS(jname)(JNIEnv *env, jclass c, jlong h, jarr out)                  \
+    {                                                                                            \
+        (void)c;                                                                                 \
+        jelem *p = (*env)->Get(env, out, NULL);                                                  \
+        int rc = cfn((ldagpu_handle)(intptr_t)h, (ctype *)p);                                    \
+        (*env)->Release(env, out, p, rc ? JNI_ABORT : 0);                                        \
+        if (rc) throw_last(env, (ldagpu_handle)(intptr_t)h);                                     \
+    }
+GETTER(getTypeTopicCounts, ldagpu_get_type_topic_counts, jintArray, jint, int32_t, GetIntArrayElements, ReleaseIntArrayElements)
+GETTER(getTopicTotals, ldagpu_get_topic_totals, jintArray, jint, int32_t, GetIntArrayElements, ReleaseIntArrayElements)
+GETTER(getPhi, ldagpu_get_phi, jdoubleArray, jdouble, double, GetDoubleArrayElements, ReleaseDoubleArrayElements)
+
+JNIEXPORT jdouble JNICALL CLS(logLikelihood)(JNIEnv *env, jclass c, jlong h)
+{
+    (void)c;
+    double v = 0.0;
+    if (ldagpu_log_likelihood((ldagpu_handle)(intptr_t)h, &v)) throw_last(env, (ldagpu_handle)(intptr_t)h);
+    return v;
+}
+
+JNIEXPORT jdouble JNICALL CLS(logPosterior)(JNIEnv *env, jclass c, jlong h)
+{
+    (void)c;
+    double v = 0.0;
+    if (ldagpu_log_posterior((ldagpu_handle)(intptr_t)h, &v)) throw_last(env, (ldagpu_handle)(intptr_t)h);
+    return v;
+}
+
+JNIEXPORT void JNICALL CLS(abort)(JNIEnv *env, jclass c, jlong h)
+{
+    (void)env; (void)c;
+    ldagpu_abort((ldagpu_handle)(intptr_t)h);
+}
