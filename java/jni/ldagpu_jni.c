@@ -29,6 +29,7 @@
  * reference's own samplers throw on an invariant break (UncollapsedParallelLDA.java:475-481,1828-1830).
  */
 #include <jni.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "ldagpu.h"
