@@ -252,6 +252,26 @@ def test_spalias_contract_vs_faithful_and_invariants(oracle):
     assert st["n_wk"].sum() == len(tokens) and np.array_equal(st["n_wk"].sum(axis=0), st["n_k"])
 
 
+def test_spalias_contract_multi_block_lists(oracle):
+    """Documents whose non-zero topic list exceeds one 256-entry block of the contract's cumulative sum
+    (random start, K = 3000, ~700-token documents): the block carries must keep the contract on the
+    faithful walk.  A single rounding flip reorders the document's list (swap-remove / append) and so
+    changes every later draw of THAT document, hence the comparison per document."""
+    off, tokens = make_corpus(12, 200, 700, seed=23)
+    V, K, beta = 200, 3000, 0.05
+    alpha = np.full(K, 0.02)
+    z = oracle.java_next_ints(7, K, len(tokens))
+    assert max(len(np.unique(z[off[d]:off[d + 1]])) for d in range(len(off) - 1)) > 2 * 256
+    n_wk, _ = oracle.rebuild_counts(tokens, z, V, K)
+    phi = oracle.phi_contract(n_wk, beta, 7, 0)
+    a = oracle.z_spalias_contract(off, tokens, z, K, alpha, phi, 7, 1)
+    b = oracle.z_spalias_faithful(off, tokens, z, K, alpha.astype(np.float32).astype(np.float64),
+                                  phi.astype(np.float64), 7, 1)
+    assert a.min() >= 0 and a.max() < K
+    same = [np.array_equal(a[off[d]:off[d + 1]], b[off[d]:off[d + 1]]) for d in range(len(off) - 1)]
+    assert sum(same) >= len(same) - 2
+
+
 def test_spalias_targets_the_same_conditional_as_dense_pcgs(oracle):
     """One token resampled many times: the sparse mixture (alias prior + sparse likelihood) and the dense
     walk must give the same distribution over topics (chi-square on a single-document corpus)."""
