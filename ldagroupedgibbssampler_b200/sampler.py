@@ -120,6 +120,15 @@ class LDAConfiguration:
         return c
 
 
+@dataclass
+class TopicAssignment:
+    """MALLET's cc.mallet.topics.TopicAssignment as the samplers use it: the document's type ids
+    (``instance``, a FeatureSequence's features) and its topic indicators (``topicSequence``)."""
+
+    instance: np.ndarray
+    topicSequence: np.ndarray
+
+
 class GpuLDASampler:
     """``LDAGibbsSampler`` + ``LDASamplerWithPhi`` for ``scheme = gpu_ggs | gpu_pcgs``."""
 
@@ -385,6 +394,14 @@ class GpuLDASampler:
 
     def getDataset(self) -> InstanceList:
         return self._data
+
+    def getData(self) -> List["TopicAssignment"]:
+        """LGS:26, MSL:42: one TopicAssignment (instance tokens + topicSequence) per local document, with the
+        CURRENT topic indicators -- the copy back into each document's LabelSequence that the Java shim does
+        after every sample() call (util/LDAUtils.java:1552-1571 and MSL:464-477,536-547 read z from there)."""
+        self._need()
+        z, off = self.get_z_flat(), self._doc_off
+        return [TopicAssignment(self._tokens[off[d]: off[d + 1]], z[off[d]: off[d + 1]]) for d in range(len(off) - 1)]
 
     def getAlphabet(self):
         return self._data.getDataAlphabet()

@@ -174,6 +174,10 @@ def test_sample_with_z_read_back_and_pipelined_set_z(oracle):
     b.sample(3)
     assert np.array_equal(zbuf, a.get_z_flat()) and np.array_equal(zbuf, b.get_z_flat())
     assert np.array_equal(a.getTypeTopicMatrix(), b.getTypeTopicMatrix())
+    data = a.getData()                                        # LGS:26: documents with their current z
+    assert len(data) == len(off) - 1 and all(len(t.instance) == len(t.topicSequence) for t in data)
+    assert np.array_equal(np.concatenate([t.topicSequence for t in data]), zbuf)
+    assert np.array_equal(np.concatenate([t.instance for t in data]), tokens)
     zbuf2 = np.zeros(len(tokens), np.int32)
     a.sample(0, z_out=zbuf2)                                  # no sweep: plain copy of the current z
     assert np.array_equal(zbuf2, zbuf)
