@@ -62,6 +62,20 @@ def test_unknown_scheme_rejected():
     assert isinstance(L.createModel(L.LDAConfiguration(scheme="gpu_pcgs", topics=4)), L.GpuLDASampler)
 
 
+def test_sampler_interface_is_complete():
+    """Every method of the reference's sampler interfaces exists on the host mirror
+    (topics/LDAGibbsSampler.java:10-47, topics/LDASamplerWithPhi.java:5-12, topics/AbortableSampler.java:3-6,
+    plus getTypeTopicCounts, UncollapsedParallelLDA.java:226-234, which tests and batch builders call)."""
+    methods = """setConfiguration getConfiguration addInstances addTestInstances sample setRandomSeed getNoTopics
+        getNumTopics getNoTypes getCurrentIteration getZIndicators getZbar getThetaEstimate setZIndicators getDataset
+        getData getDeltaStatistics getTopTypeFrequencyIndices getTypeFrequencies getCorpusSize getAlphabet getStartSeed
+        getTypeMassCumSum getDocumentTopicMatrix getTypeTopicMatrix getTopicTotals getBeta getAlpha preIteration
+        postIteration preSample postSample postZ preZ getLogLikelihood getHeldOutLogLikelihood abort getAbort
+        getPhi setPhi getPhiMeans prePhi postPhi sampleZGivenPhi getTypeTopicCounts""".split()
+    missing = [m for m in methods if not callable(getattr(L.GpuLDASampler, m, None))]
+    assert not missing, missing
+
+
 def test_cfg_parsing(tmp_path):
     # shape of src/main/resources/configuration/plda-cats-test.cfg
     p = tmp_path / "t.cfg"
