@@ -1,21 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- token-topic samples/sec of one Gibbs sweep (BASELINE.json metric) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload pubmed8|nips|enron]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload pubmed|pubmed8|nips|enron|wiki8] [--scaling strong|weak]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...      # the CPU port of the reference's sampler, same metric
+    python bench.py --impl reference ...      # the CPU port of the reference's sampler, same metric and config
 
-A "step" is one full sweep ([theta] z, count rebuild, [exchange], Phi draw) over the rank's shard.
-Default workload: PubMed-shaped GGS, K=1000, V=141043, one eighth of the 8.2M-document corpus per GPU
-(weak scaling: at 8 GPUs it is exactly BASELINE.json configs[3]); Phi^T is 577 MB, larger than the
-126 MB L2, so no L2 flush is needed between steps.
+A "step" is one full sweep ([theta +] z with the count rebuild, [exchange], Phi draw) over the corpus.
+Default workload: BASELINE.json configs[3] -- the WHOLE PubMed-shaped corpus (8.2 M documents, ~738 M tokens,
+V = 141 043), GGS K = 1000.  It fits one B200 (tokens + z 5.9 GB, theta 33.6 GB, Phi^T + n_wk 1.2 GB), so N = 1
+runs all of it and N GPUs share the same fixed corpus: `scaling` is "strong".  Phi^T is 578 MB, larger than the
+126 MB L2, so no L2 flush is needed between steps.  `--workload pubmed8 / wiki8` keep the round-1 weak-scaling
+shards (one eighth of the corpus per GPU).
 
 value   device-resident: K sweeps inside ONE ldagpu_sweep call, timed with CUDA events on the library's
         stream, max over ranks.
 e2e     the same metric through the sampler API with host buffers: every step uploads z from pinned
         host memory (setZIndicators path, keeps Phi), runs sample(1, z_out=...) which reads z back, and
-        reads the topic totals.
+        reads the topic totals.  K <= 65 536: z travels as uint16 (ldagpu_set_z16 / ldagpu_sweep_get_z16).
 """
 from __future__ import annotations
 
@@ -33,16 +35,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # per-GPU shard; D scales with the number of GPUs (weak scaling)
+    # D = documents of the WHOLE corpus for scaling "strong", documents per GPU for scaling "weak"
+    "pubmed": dict(desc="PubMed-shaped GGS K=1000, V=141043, the whole 8.2M-doc corpus (BASELINE.json configs[3])",
+                   D=8200000, V=141043, mean_len=90.0, K=1000, scheme="gpu_ggs", alpha=0.05, beta=0.01, scaling="strong"),
     "pubmed8": dict(desc="PubMed-shaped GGS K=1000, V=141043, per-GPU shard = 1/8 of the 8.2M-doc corpus",
-                    D=1025000, V=141043, mean_len=90.0, K=1000, scheme="gpu_ggs", alpha=0.05, beta=0.01),
+                    D=1025000, V=141043, mean_len=90.0, K=1000, scheme="gpu_ggs", alpha=0.05, beta=0.01, scaling="weak"),
     "nips": dict(desc="NIPS-shaped GGS K=100 (BASELINE.json configs[1])",
-                 D=1500, V=12419, mean_len=1267.0, K=100, scheme="gpu_ggs", alpha=1.0, beta=0.01),
+                 D=1500, V=12419, mean_len=1267.0, K=100, scheme="gpu_ggs", alpha=1.0, beta=0.01, scaling="strong"),
     "enron": dict(desc="Enron-shaped PCGS K=400 (BASELINE.json configs[2])",
-                  D=39861, V=28102, mean_len=161.0, K=400, scheme="gpu_pcgs", alpha=0.125, beta=0.01),
+                  D=39861, V=28102, mean_len=161.0, K=400, scheme="gpu_pcgs", alpha=0.125, beta=0.01, scaling="strong"),
     "wiki8": dict(desc="Wikipedia-shaped sparse PCGS K=10000, V=100000, per-GPU shard = 1/8 of the ~4M-doc corpus "
                        "(BASELINE.json configs[4] at 8 GPUs)",
-                  D=500000, V=100000, mean_len=250.0, K=10000, scheme="gpu_spalias", alpha=0.005, beta=0.01),
+                  D=500000, V=100000, mean_len=250.0, K=10000, scheme="gpu_spalias", alpha=0.005, beta=0.01, scaling="weak"),
 }
 METRIC = "token-topic samples/sec per Gibbs sweep"
 UNIT = "tokens/s"
@@ -57,14 +61,27 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def traffic_from_profiles(workload):
-    """dram bytes per z-kernel launch from the committed ncu capture, if there is one for this workload."""
+def profile_record(workload):
+    """What the committed `ncu --set full` capture of the z-step kernel says for this workload shape
+    (profiles/z_kernel_traffic.json: DRAM and L2->SM bytes per token, the binding unit).  None when there is no
+    capture for the shape."""
     p = os.path.join(ROOT, "profiles", "z_kernel_traffic.json")
     if os.path.exists(p):
-        t = json.load(open(p)).get(workload)
-        if t:
-            return t.get("dram_bytes_per_launch")
+        return json.load(open(p)).get(workload)
     return None
+
+
+def make_config(name, wl, scaling):
+    """Identical keys in both arms (ours and --impl reference)."""
+    ks = (wl["K"] + 31) // 32 * 32
+    return {"workload": wl["desc"], "name": name, "scheme": wl["scheme"], "K": wl["K"], "V": wl["V"],
+            "docs": wl["D"], "docs_are": "whole corpus" if scaling == "strong" else "per GPU",
+            "mean_doc_len": wl["mean_len"], "alpha": wl["alpha"], "beta": wl["beta"], "scaling": scaling,
+            "corpus_seed": CORPUS_SEED, "seed": SEED,
+            "l2": ("inputs larger than L2 (Phi^T %.0f MB, corpus + theta several GB), no flush"
+                   if wl["V"] * 4 * wl["K"] > 126e6 else
+                   "Phi^T %.0f MB is L2-resident, no flush -- the HBM roofline is a loose bound here")
+                  % (wl["V"] * 4 * ks / 1e6)}
 
 
 class ClockSampler:
@@ -112,12 +129,36 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline(wl, off, tokens, budget_tokens, n_shard_tokens):
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank's host thread (and so the first touch of its pinned buffers) on the NUMA node of its GPU."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        bdf = out[-12:] if len(out) >= 12 else out          # 00000000:1b:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
+def cpu_baseline(wl, off, tokens, budget_tokens, n_total_tokens, threads):
     """The reference's sampler restated on the CPU (oracle, faithful mode, the reference's threading
-    shape) on a bounded sample: whole documents up to `budget_tokens` tokens, one sweep, all host
+    shape) on a bounded sample: whole documents up to `budget_tokens` tokens, one sweep, `threads` host
     threads.  z cost is per token, Phi cost is per sweep (K*V Gammas, independent of the sample), so
-    the shard-level rate is N / (N * z_sec_per_token + phi_sec)."""
+    the rate on the whole workload is N / (N * z_sec_per_token + phi_sec): an EXTRAPOLATION, flagged as such.
+    Returns (record, wall seconds of this sample)."""
     from oracle import oracle as O
+    w0 = time.perf_counter()
     d1 = int(np.searchsorted(off, budget_tokens, side="right")) - 1
     d1 = max(1, min(d1, len(off) - 1))
     o, t = off[: d1 + 1].copy(), tokens[: off[d1]].copy()
@@ -140,21 +181,50 @@ def cpu_baseline(wl, off, tokens, budget_tokens, n_shard_tokens):
         zs = max(time.perf_counter() - t0 - ab, 1e-9)
         nt = O.lib().oracle_max_threads()
         per_tok = zs / max(len(t), 1)
-        value = n_shard_tokens / (n_shard_tokens * per_tok + ps + ab)
-        return {"value": value, "unit": UNIT, "cores": nt, "kind": "port",
-                "sample": f"{d1} documents / {len(t)} tokens of the same corpus, 1 sweep of the sparse sampler: "
-                          f"token loop {zs:.3f}s ({per_tok * 1e9:.1f} ns/token), alias tables {ab:.3f}s and Phi draw "
-                          f"{ps:.3f}s (both full K*V); rate extrapolated to the {n_shard_tokens}-token shard; C "
-                          f"restatement (oracle/lda_oracle_sparse.c), not the Java reference"}
-    sch = O.GGS if wl["scheme"] == "gpu_ggs" else O.PCGS
-    zs, ps, nt = O.baseline_sweeps(sch, o, t, z, V, K, np.full(K, wl["alpha"]), wl["beta"], SEED, 1)
-    per_tok = zs / max(len(t), 1)
-    value = n_shard_tokens / (n_shard_tokens * per_tok + ps)
-    return {"value": value, "unit": UNIT, "cores": nt, "kind": "port",
-            "sample": f"{d1} documents / {len(t)} tokens of the same corpus, 1 sweep: z+merge {zs:.3f}s "
-                      f"({per_tok * 1e9:.1f} ns/token), Phi draw {ps:.3f}s (full K*V); rate extrapolated to "
-                      f"the {n_shard_tokens}-token shard; no JDK in the image, so this is the C restatement "
-                      f"(oracle/lda_oracle.c oracle_baseline_sweeps), not the Java reference"}
+        value = n_total_tokens / (n_total_tokens * per_tok + ps + ab)
+        what = (f"token loop {zs:.3f}s ({per_tok * 1e9:.1f} ns/token), alias tables {ab:.3f}s and Phi draw {ps:.3f}s "
+                f"(both full K*V); C restatement (oracle/lda_oracle_sparse.c)")
+    else:
+        sch = O.GGS if wl["scheme"] == "gpu_ggs" else O.PCGS
+        zs, ps, nt = O.baseline_sweeps(sch, o, t, z, V, K, np.full(K, wl["alpha"]), wl["beta"], SEED, 1, n_threads=threads)
+        per_tok = zs / max(len(t), 1)
+        value = n_total_tokens / (n_total_tokens * per_tok + ps)
+        what = (f"z+merge {zs:.3f}s ({per_tok * 1e9:.1f} ns/token), Phi draw {ps:.3f}s (full K*V); C restatement "
+                f"(oracle/lda_oracle.c oracle_baseline_sweeps)")
+    rec = {"value": value, "unit": UNIT, "cores": nt, "kind": "port", "extrapolated": True,
+           "sample": f"{d1} documents / {len(t)} tokens of the same corpus, 1 sweep: {what}; rate extrapolated to the "
+                     f"{n_total_tokens}-token workload; no JDK in the image, so this is the C port, not the Java reference"}
+    return rec, time.perf_counter() - w0
+
+
+def reference_arm(args, name, wl, scaling):
+    """--impl reference: the reference's own CPU implementation of the path (C port of the Java sampler; no JDK in
+    the image) on all host threads, rank 0 only.  Loads the oracle and the host-only corpus generator -- never
+    libldagpu.so."""
+    threads = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(threads)      # torchrun exports OMP_NUM_THREADS=1 to its workers
+    os.environ.pop("OMP_PROC_BIND", None)
+    from ldagroupedgibbssampler_b200._lib import synth_corpus
+    n_gpus = max(args.gpus, 1)
+    docs_total = wl["D"] * (n_gpus if scaling == "weak" else 1)
+    n_total = int(round(docs_total * wl["mean_len"]))
+    sample_docs = int(min(wl["D"], max(2000, 1.3 * args.cpu_sample_tokens / wl["mean_len"])))
+    off, tokens = synth_corpus(sample_docs, wl["V"], wl["mean_len"], seed=CORPUS_SEED)
+    vals, walls = [], []
+    for i in range(args.warmup + args.steps):
+        r, wall = cpu_baseline(wl, off, tokens, args.cpu_sample_tokens, n_total, threads)
+        if i >= args.warmup:
+            vals.append(r); walls.append(wall)
+    v = float(np.mean([x["value"] for x in vals]))
+    cb = dict(vals[-1]); cb["value"] = v
+    return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * float(np.mean(walls)), "ms_per_step_is": "wall time of one bounded-sample step "
+            "(the extrapolated whole-workload sweep would take %.1f s)" % (n_total / v),
+            "extrapolated": True, "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": make_config(name, wl, scaling),
+            "cpu_baseline": cb,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
 def main():
@@ -163,9 +233,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="pubmed8", choices=sorted(WORKLOADS))
-    ap.add_argument("--docs", type=int, default=0, help="override documents per GPU (debugging)")
+    ap.add_argument("--workload", default="pubmed", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default=None, choices=["strong", "weak"],
+                    help="strong: N GPUs share the workload's documents; weak: every GPU gets that many (default per workload)")
+    ap.add_argument("--docs", type=int, default=0, help="override the workload's document count (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="N=1: skip the NIPS-/Enron-/Wikipedia-shaped side measurements")
     ap.add_argument("--cpu-sample-tokens", type=int, default=3_000_000)
     args = ap.parse_args()
 
@@ -175,43 +248,21 @@ def main():
     wl = dict(WORKLOADS[args.workload])
     if args.docs:
         wl["D"] = args.docs
-    config = {"workload": wl["desc"], "scheme": wl["scheme"], "K": wl["K"], "V": wl["V"],
-              "docs_per_gpu": wl["D"], "alpha": wl["alpha"], "beta": wl["beta"],
-              "l2": ("inputs larger than L2 (Phi^T %.0f MB, corpus + theta several GB), no flush"
-                     if wl["V"] * 4 * wl["K"] > 126e6 else
-                     "secondary workload: Phi^T %.0f MB is L2-resident, no flush -- HBM roofline is a loose bound here")
-                    % (wl["V"] * 4 * ((wl["K"] + 31) // 32 * 32) / 1e6)}
+    scaling = args.scaling or wl["scaling"]
 
-    import ldagroupedgibbssampler_b200 as L
-
-    # ----------------------------------------------------------------------------------------
     if args.impl == "reference":
-        # the reference's own CPU implementation of the path (C port; no JDK in the image), rank 0 only
-        if rank != 0:
-            return
-        off, tokens = L.synth_corpus(min(wl["D"], 60000), wl["V"], wl["mean_len"], seed=CORPUS_SEED)
-        n_shard = int(round(wl["D"] * wl["mean_len"])) * max(args.gpus, 1)
-        vals = []
-        for i in range(args.warmup + args.steps):
-            r = cpu_baseline(wl, off, tokens, args.cpu_sample_tokens // 3, n_shard)
-            if i >= args.warmup:
-                vals.append(r)
-        v = float(np.mean([x["value"] for x in vals]))
-        cb = dict(vals[-1]); cb["value"] = v
-        return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * n_shard / v, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                "cpu_baseline": cb,
-                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        return reference_arm(args, args.workload, wl, scaling) if rank == 0 else None
 
     # ----------------------------------------------------------------------------------------
     import torch
     import torch.distributed as dist
 
+    import ldagroupedgibbssampler_b200 as L
+
     if world > 1:
         dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
 
     def barrier():
         torch.cuda.synchronize()
@@ -225,136 +276,197 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def all_sum(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    def measure(name, wl, scaling, steps, warmup, with_e2e, with_clocks):
+        """One workload on this process group: device-resident sweeps, then the end-to-end loop."""
+        if scaling == "strong":
+            d0, d1 = wl["D"] * rank // world, wl["D"] * (rank + 1) // world      # this rank's documents of the fixed corpus
+        else:
+            d0, d1 = rank * wl["D"], (rank + 1) * wl["D"]
+        t0 = time.time()
+        off, tokens = L.synth_corpus(d1 - d0, wl["V"], wl["mean_len"], seed=CORPUS_SEED, doc_first=d0)
+        n_local = len(tokens)
+        if world > 1:
+            sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+            dist.all_gather(sizes, torch.tensor([n_local], dtype=torch.int64, device="cuda"))
+            sizes = [int(s.item()) for s in sizes]
+        else:
+            sizes = [n_local]
+        token_base, n_total = sum(sizes[:rank]), sum(sizes)
+        gen_s = time.time() - t0
 
-    # this rank's shard of the global corpus (documents [rank*D, (rank+1)*D))
-    t0 = time.time()
-    off, tokens = L.synth_corpus(wl["D"], wl["V"], wl["mean_len"], seed=CORPUS_SEED, doc_first=rank * wl["D"])
-    n_local = len(tokens)
-    if world > 1:
-        sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-        dist.all_gather(sizes, torch.tensor([n_local], dtype=torch.int64, device="cuda"))
-        sizes = [int(s.item()) for s in sizes]
-    else:
-        sizes = [n_local]
-    token_base, n_total = sum(sizes[:rank]), sum(sizes)
-    gen_s = time.time() - t0
+        cfg = L.LDAConfiguration(scheme=wl["scheme"], topics=wl["K"], alpha=wl["alpha"], beta=wl["beta"], seed=SEED,
+                                 exec_time=0)
+        s = L.GpuLDASampler(cfg, device=local_rank)
+        comm_id = None
+        if world > 1:
+            box = [L.GpuLDASampler.make_comm_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            comm_id = box[0]
+        s.addInstances(L.InstanceList.from_csr(off, tokens, wl["V"]), rank=rank, world=world, comm_id=comm_id,
+                       presharded=(d0, token_base, n_total))
 
-    cfg = L.LDAConfiguration(scheme=wl["scheme"], topics=wl["K"], alpha=wl["alpha"], beta=wl["beta"], seed=SEED,
-                             exec_time=0)
-    s = L.GpuLDASampler(cfg, device=local_rank)
-    comm_id = None
-    if world > 1:
-        box = [L.GpuLDASampler.make_comm_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        comm_id = box[0]
-    s.addInstances(L.InstanceList.from_csr(off, tokens, wl["V"]), rank=rank, world=world, comm_id=comm_id,
-                   presharded=(rank * wl["D"], token_base, n_total))
-
-    # ---- device-resident: warm-up, then exactly K sweeps in one library call ---------------
-    s.sample(args.warmup)
-    clocks = ClockSampler()
-    barrier()
-    if rank == 0:
-        clocks.start()
-    w0 = time.perf_counter()
-    s.sample(args.steps)
-    barrier()
-    wall_ms = (time.perf_counter() - w0) * 1e3
-    call_ms, zk_ms, zk_launches, launches = s.getLastCallStats()
-    ck = clocks.stop(set(range(world))) if rank == 0 else None
-    need_more = 1.0 if (rank == 0 and (ck.get("samples") or 0) < 3) else 0.0
-    wall_ms = all_max(wall_ms)
-    if all_max(need_more) > 0:
-        # the timed region was shorter than nvidia-smi's sampling period (small workloads): sample the clocks
-        # over an untimed repeat of the same sweeps, long enough for a few samples
-        reps = max(args.steps, int(0.8 / max(wall_ms / 1e3 / args.steps, 1e-6)))
-        clocks2 = ClockSampler()
+        # ---- device-resident: warm-up, then exactly K sweeps in one library call ---------------
+        s.sample(warmup, chunk=0)
+        clocks = ClockSampler()
         barrier()
-        if rank == 0:
-            clocks2.start()
-            time.sleep(0.15)
-        s.sample(reps)
+        if rank == 0 and with_clocks:
+            clocks.start()
+        w0 = time.perf_counter()
+        s.sample(steps, chunk=0)
         barrier()
-        if rank == 0:
-            ck = clocks2.stop(set(range(world)))
-            ck["note"] = (f"timed region ({wall_ms:.1f} ms) shorter than the sampling period: clocks sampled over an "
-                          f"untimed repeat of {reps} sweeps of the same workload")
-    dev_ms = all_max(call_ms)
-    zk_ms_per_launch = all_max(zk_ms / max(zk_launches, 1))
-    value = n_total * args.steps / (dev_ms / 1e3)
+        wall_ms = (time.perf_counter() - w0) * 1e3
+        call_ms, zk_ms, zk_launches, launches = s.getLastCallStats()
+        ck = clocks.stop(set(range(world))) if (rank == 0 and with_clocks) else None
+        need_more = 1.0 if (rank == 0 and with_clocks and (ck.get("samples") or 0) < 3) else 0.0
+        wall_ms = all_max(wall_ms)
+        if all_max(need_more) > 0:
+            # the timed region was shorter than nvidia-smi's sampling period (small workloads): sample the clocks
+            # over an untimed repeat of the same sweeps, long enough for a few samples
+            reps = max(steps, int(0.8 / max(wall_ms / 1e3 / steps, 1e-6)))
+            clocks2 = ClockSampler()
+            barrier()
+            if rank == 0:
+                clocks2.start()
+                time.sleep(0.15)
+            s.sample(reps, chunk=0)
+            barrier()
+            if rank == 0:
+                ck = clocks2.stop(set(range(world)))
+                ck["note"] = (f"timed region ({wall_ms:.1f} ms) shorter than the sampling period: clocks sampled over an "
+                              f"untimed repeat of {reps} sweeps of the same workload")
+        dev_ms = all_max(call_ms)
+        zk_ms_per_launch = all_max(zk_ms / max(zk_launches, 1))
+        res = {"value": n_total * steps / (dev_ms / 1e3), "ms_per_step": dev_ms / steps, "clocks": ck,
+               "launches": int(launches), "zk_ms_per_launch": zk_ms_per_launch, "zk_share": zk_ms / max(call_ms, 1e-9),
+               "n_total": n_total, "sizes": sizes, "gen_s": gen_s, "wall_ms_per_step": wall_ms / steps,
+               "exchange": s.getExchangeMode(), "timers": dict(zip(("z", "counts", "phi", "comm"), s.getTimers()))}
 
-    # ---- end to end through the sampler API with pinned host buffers -----------------------
-    zbuf = torch.empty(max(n_local, 1), dtype=torch.int32, pin_memory=True)
-    znp = zbuf.numpy()[:n_local]
-    znp[:] = s.get_z_flat()
-    import ctypes as C
-    lib = L.load()
+        # ---- roofline inputs: how many Phi^T row fetches a token costs on this corpus ------------------------
+        ns = min(n_local, 30_000_000)
+        if ns > 1:
+            ds = int(np.searchsorted(off, ns, side="right")) - 1
+            ns = int(off[ds])
+            tk = tokens[:ns]
+            pos = np.arange(ns, dtype=np.int64) - np.repeat(off[:ds], np.diff(off[: ds + 1]))
+            head = np.ones(ns, bool)
+            head[1:] = tk[1:] != tk[:-1]
+            head |= (pos & 31) == 0        # a run ends at the 32-token block of the warp
+            res["fetches_per_token"] = float(head.mean())
+        mean_nnz = None
+        if wl["scheme"] == "gpu_spalias":
+            # SURVEY 8(d) sparse z-step: 12 + 8*nnz_d + 16 bytes per token, nnz_d measured on a sample of documents
+            zf, dsamp = s.get_z_flat(), min(len(off) - 1, 20000)
+            nnz = np.array([len(np.unique(zf[off[d]:off[d + 1]])) for d in range(dsamp)], np.float64)
+            lens = np.diff(off[: dsamp + 1]).astype(np.float64)
+            mean_nnz = float((nnz * lens).sum() / max(lens.sum(), 1.0))
+        res["mean_nnz"] = mean_nnz
 
-    def e2e_step():
-        s._ck(lib.ldagpu_set_z(s._h, C.c_void_p(zbuf.data_ptr()), 0))        # H2D z (+ count rebuild, Phi kept)
-        s.sample(1, z_out=znp)                                              # sweep; D2H z under the Phi draw
-        return s.getTopicTotals()                                           # D2H n_k
+        # ---- end to end through the sampler API with pinned host buffers -----------------------
+        if with_e2e:
+            z16 = wl["K"] <= 65536
+            zbuf = torch.empty(max(n_local, 1), dtype=torch.uint16 if z16 else torch.int32, pin_memory=True)
+            znp = zbuf.numpy()[:n_local]
+            znp[:] = s.get_z_flat().astype(znp.dtype)
+            import ctypes as C
+            lib = L.load()
+            set_z = lib.ldagpu_set_z16 if z16 else lib.ldagpu_set_z
 
-    for _ in range(max(1, min(args.warmup, 2))):
-        e2e_step()
-    barrier()
-    e0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    e2e_ms = all_max((time.perf_counter() - e0) * 1e3)
-    e2e_value = n_total * args.steps / (e2e_ms / 1e3)
+            def e2e_step():
+                s._ck(set_z(s._h, C.c_void_p(zbuf.data_ptr()), 0))                 # H2D z (+ count rebuild, Phi kept)
+                s.sample(1, z_out=znp, chunk=0)                                     # sweep; D2H z under the Phi draw
+                return s.getTopicTotals()                                           # D2H n_k
 
-    # ---- roofline of the dominant kernel (z-step) -------------------------------------------
+            for _ in range(max(1, min(warmup, 2))):
+                e2e_step()
+            barrier()
+            e0 = time.perf_counter()
+            for _ in range(steps):
+                e2e_step()
+            barrier()
+            e2e_ms = all_max((time.perf_counter() - e0) * 1e3)
+            esz = 2 if z16 else 4
+            res["e2e"] = {"value": n_total * steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": esz * n_local,
+                          "d2h_bytes_per_step": esz * n_local + 4 * wl["K"], "ms_per_step": e2e_ms / steps,
+                          "z_dtype": "uint16" if z16 else "int32", "numa_node": numa,
+                          "what": "per step: ldagpu_set_z16 from pinned host z (upload pipelined with the widening and the "
+                                  "count rebuild), sample(1, z_out=pinned host z) = ldagpu_sweep_get_z16 (z narrowed and read "
+                                  "back while the Phi draw runs), getTopicTotals; host wall clock, max over ranks; bytes are "
+                                  "per rank"}
+        s.close()
+        return res, off, tokens
+
+    config = make_config(args.workload, wl, scaling)
+    res, off, tokens = measure(args.workload, wl, scaling, args.steps, args.warmup, True, True)
+
+    # ---- roofline of the dominant kernel (z-step; GGS: with the fused theta draw) ---------------------
     peak, peak_src = peaks()
-    bytes_per_token = 4 * wl["K"] + 12                      # one fp32 K-vector + w + z in + z out
-    mean_nnz = None
-    if wl["scheme"] == "gpu_spalias":
-        # SURVEY 8(d) sparse z-step: 12 + 8*nnz_d + 16 bytes per token, nnz_d measured on a sample of documents
-        zf, dsamp = s.get_z_flat(), min(len(off) - 1, 20000)
-        nnz = np.array([len(np.unique(zf[off[d]:off[d + 1]])) for d in range(dsamp)], np.float64)
-        lens = np.diff(off[: dsamp + 1]).astype(np.float64)
-        mean_nnz = float((nnz * lens).sum() / max(lens.sum(), 1.0))
-        bytes_per_token = 28 + 8 * mean_nnz
-    alg_bytes = bytes_per_token * max(sizes)                # one launch processes the rank's shard
-    achieved = alg_bytes / (zk_ms_per_launch / 1e3) / 1e9
-    traffic = traffic_from_profiles(args.workload)
-    roofline = {"bound": "hbm", "kernel": "z_spalias_kernel" if mean_nnz is not None else "z_kernel",
-                "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "mean_nnz_d": mean_nnz,
-                "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_token": bytes_per_token,
-                "kernel_ms_per_launch": zk_ms_per_launch, "kernel_share_of_step": zk_ms / max(call_ms, 1e-9),
-                "traffic": traffic,
-                "note": "algorithmic bytes charge one fp32 K-vector of Phi^T per token (SURVEY 8d); a run of equal "
-                        "word types shares one fetch and the Zipf vocabulary keeps hot rows in the 126 MB L2, so "
-                        "the DRAM traffic (ncu, `traffic`) is far below it and frac can exceed 1: the kernel is "
-                        "issue/shared-pipe bound, not HBM bound (DESIGN.md section 5)"}
+    n_launch = max(res["sizes"])                               # one launch processes the rank's tokens
+    t_s = res["zk_ms_per_launch"] / 1e3
+    ks = (wl["K"] + 127) // 128 * 128 if wl["K"] <= 1024 else (wl["K"] + 31) // 32 * 32
+    prof = profile_record(args.workload) or {}
+    if res["mean_nnz"] is not None:
+        bytes_per_token = 28 + 8 * res["mean_nnz"]
+        kernel = "z_spalias_kernel"
+    else:
+        bytes_per_token = 4 * wl["K"] + 12                      # SURVEY 8(d): one fp32 K-vector + w + z in + z out
+        kernel = "z_kernel"
+    model_bytes = bytes_per_token * n_launch
+    dram_pt = prof.get("dram_bytes_per_token")
+    traffic = dram_pt * n_launch if dram_pt else None
+    achieved = (traffic / t_s / 1e9) if traffic else None
+    fpt = res.get("fetches_per_token")
+    roofline = {"bound": "hbm", "kernel": kernel, "unit": "GB/s", "peak": peak, "peak_source": peak_src,
+                "achieved": achieved, "frac": (achieved / peak) if achieved else None,
+                "achieved_is": "DRAM bytes the kernel really moves (ncu dram__bytes_read+write per token of the committed "
+                               "capture of this kernel on this workload shape, x the tokens of one launch) / the launch "
+                               "duration measured live with CUDA events" if achieved else
+                               "no committed ncu capture for this workload shape: frac left null rather than guessed",
+                "traffic": traffic, "traffic_source": prof.get("source"),
+                "kernel_ms_per_launch": res["zk_ms_per_launch"], "kernel_share_of_step": res["zk_share"],
+                "achieved_model": model_bytes / t_s / 1e9, "frac_model": model_bytes / t_s / 1e9 / peak,
+                "model": "SURVEY 8(d) algorithmic figure: %.0f bytes per token x %d tokens per launch; it charges one Phi^T "
+                         "row per TOKEN, so it exceeds the HBM peak whenever rows are shared or cached -- kept for "
+                         "reference, not a roofline fraction" % (bytes_per_token, n_launch),
+                "algorithmic_bytes_per_launch": model_bytes, "bytes_per_token": bytes_per_token,
+                "mean_nnz_d": res["mean_nnz"], "fetches_per_token": fpt,
+                "dedup_bytes": (fpt * 4 * ks * n_launch) if (fpt and res["mean_nnz"] is None) else None,
+                "dedup_is": "row fetches the kernel issues (one per run of equal word types inside a 32-token block, "
+                            "counted on this corpus) x 4*Ks bytes: the L2->SM traffic of the launch",
+                "binding": prof.get("binding")}
+    if roofline["dedup_bytes"]:
+        roofline["l2_to_sm_gbs"] = roofline["dedup_bytes"] / t_s / 1e9
 
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": dict(config, exchange=s.getExchangeMode(), tokens_total=n_total, tokens_per_gpu=sizes,
-                          corpus_gen_s=round(gen_s, 1),
-                          wall_ms_per_step=wall_ms / args.steps),
-           "clocks": ck,
-           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n_local,
-                   "d2h_bytes_per_step": 4 * n_local + 4 * wl["K"], "ms_per_step": e2e_ms / args.steps,
-                   "what": "per step: ldagpu_set_z from pinned host z (upload pipelined with the count rebuild), "
-                           "sample(1, z_out=pinned host z) (z read back while the Phi draw runs), getTopicTotals; "
-                           "host wall clock, max over ranks"},
-           "gpu_launches": int(launches),
-           "roofline": roofline,
-           "timers_ms": dict(zip(("z", "counts", "phi", "comm"), s.getTimers()))}
+    out = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+           "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": config,
+           "run": {"exchange": res["exchange"], "tokens_total": res["n_total"], "tokens_per_gpu": res["sizes"],
+                   "corpus_gen_s": round(res["gen_s"], 1), "wall_ms_per_step": res["wall_ms_per_step"]},
+           "clocks": res["clocks"], "e2e": res["e2e"], "gpu_launches": res["launches"], "roofline": roofline,
+           "timers_ms": res["timers"]}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(wl, off, tokens, args.cpu_sample_tokens, n_total)
-    s.close()
+        out["cpu_baseline"], _ = cpu_baseline(wl, off, tokens, args.cpu_sample_tokens, res["n_total"], os.cpu_count() or 1)
+    del off, tokens
+
+    # ---- the other BASELINE.json configs on one GPU, measured in the same run (N = 1 only) ------------------------
+    if world == 1 and not args.no_secondary and not args.docs:
+        sec = {}
+        for nm in ("nips", "enron", "wiki8"):
+            if nm == args.workload:
+                continue
+            w2 = dict(WORKLOADS[nm])
+            try:
+                r2, _, _ = measure(nm, w2, w2["scaling"], 50 if nm != "wiki8" else 5, 5 if nm != "wiki8" else 2,
+                                   False, False)
+                sec[nm] = {"config": make_config(nm, w2, w2["scaling"]), "value": r2["value"], "unit": UNIT,
+                           "ms_per_step": r2["ms_per_step"], "steps": 50 if nm != "wiki8" else 5,
+                           "tokens_total": r2["n_total"], "z_kernel_ms_per_launch": r2["zk_ms_per_launch"],
+                           "fetches_per_token": r2.get("fetches_per_token"), "mean_nnz_d": r2["mean_nnz"]}
+            except Exception as e:   # a side measurement must not take the headline down with it
+                sec[nm] = {"error": str(e)[:200]}
+        out["secondary"] = sec
+
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -79,7 +79,9 @@ int ldagpu_get_exchange_mode(ldagpu_handle h, int32_t *mode);
  * Rebuilds the counts and draws the initial Phi (UPL:450,1287-1294) with sweep counter 0. */
 int ldagpu_init_z_java_random(ldagpu_handle h, int32_t seed);
 /* setZIndicators (LGS:22, UPL:1797-1843): replace z, rebuild counts, redraw Phi (sweep counter
- * unchanged).  redraw_phi = 0 keeps the current Phi (used by tests and by checkpoint restore). */
+ * unchanged).  redraw_phi = 0 keeps the current Phi (used by tests and by checkpoint restore).
+ * An indicator outside [0, K) fails the call and leaves the previous indicators and counts in place (the reference
+ * throws, UPL:475-481). */
 int ldagpu_set_z(ldagpu_handle h, const int32_t *z, int32_t redraw_phi);
 /* getZIndicators (LGS:19, MSL:464-477) flattened in CSR order */
 int ldagpu_get_z(ldagpu_handle h, int32_t *z);
@@ -92,6 +94,12 @@ int ldagpu_sweep(ldagpu_handle h, int32_t n, int32_t *done);
  * This is what the Java shim's sample() does: z goes back into the documents' LabelSequences after every call
  * (MSL:464-477, util/LDAUtils.java:1552-1571 read it from there). */
 int ldagpu_sweep_get_z(ldagpu_handle h, int32_t n, int32_t *done, int32_t *z);
+/* 16-bit transport of the topic indicators (K <= 65 536): the same three calls with uint16 host buffers.
+ * The Java int[] boundary keeps the int32 entry points (MSL:464-477, UPL:1797-1843); a host that can hold z as
+ * char[] / short[] halves the PCIe bytes of every setZIndicators / sample() round trip. */
+int ldagpu_set_z16(ldagpu_handle h, const uint16_t *z, int32_t redraw_phi);
+int ldagpu_get_z16(ldagpu_handle h, uint16_t *z);
+int ldagpu_sweep_get_z16(ldagpu_handle h, int32_t n, int32_t *done, uint16_t *z);
 /* sampleZGivenPhi(iterations) (LSWP:11, UPL:975-1014): z and counts only, Phi frozen */
 int ldagpu_sample_z_given_phi(ldagpu_handle h, int32_t n, int32_t *done);
 /* step-wise entry points (tests, and hosts that interleave their own hooks preZ/postZ/prePhi/postPhi,
@@ -139,15 +147,6 @@ int ldagpu_get_timers(ldagpu_handle h, double *z_ms, double *counts_ms, double *
  * launches), and how many kernels the call launched */
 int ldagpu_get_last_call_stats(ldagpu_handle h, double *call_ms, double *z_kernel_ms,
                                int64_t *z_kernel_launches, int64_t *total_launches);
-
-/* host-side helper for benchmarks and tests: LDA-generative synthetic corpus of a given shape
- * (SURVEY 8d).  doc_offsets int64[D+1] out; tokens int32[capacity] out; returns N in *n_tokens.
- * Tokens of a document are sorted by type id (bag of words, like the bundled corpora).
- * Generates documents [doc_first, doc_first + D) of the corpus that seed defines, so ranks can
- * build their own shard. */
-int ldagpu_synth_corpus(int64_t D, int64_t doc_first, int32_t V, int32_t K_gen, double mean_len,
-                        double sigma_len, int32_t max_len, uint64_t seed, int64_t *doc_offsets,
-                        int32_t *tokens, int64_t capacity, int64_t *n_tokens);
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,8 @@ SYMBOLS = [
     "ldagpu_get_topic_totals", "ldagpu_get_doc_topic_counts", "ldagpu_get_phi", "ldagpu_set_phi",
     "ldagpu_set_phi_mean_schedule", "ldagpu_get_phi_mean", "ldagpu_get_theta", "ldagpu_set_theta",
     "ldagpu_log_likelihood", "ldagpu_log_posterior", "ldagpu_abort", "ldagpu_get_abort",
-    "ldagpu_get_timers", "ldagpu_get_last_call_stats", "ldagpu_synth_corpus",
+    "ldagpu_get_timers", "ldagpu_get_last_call_stats",
+    "ldagpu_set_z16", "ldagpu_get_z16", "ldagpu_sweep_get_z16",
 ]
 
 
@@ -59,6 +60,9 @@ def load() -> C.CDLL:
     sig("ldagpu_init_z_java_random", C.c_int, vp, i32)
     sig("ldagpu_set_z", C.c_int, vp, vp, i32)
     sig("ldagpu_get_z", C.c_int, vp, vp)
+    sig("ldagpu_set_z16", C.c_int, vp, vp, i32)
+    sig("ldagpu_get_z16", C.c_int, vp, vp)
+    sig("ldagpu_sweep_get_z16", C.c_int, vp, i32, pi32, vp)
     sig("ldagpu_sweep", C.c_int, vp, i32, pi32)
     sig("ldagpu_sweep_get_z", C.c_int, vp, i32, pi32, vp)
     sig("ldagpu_sample_z_given_phi", C.c_int, vp, i32, pi32)
@@ -78,7 +82,6 @@ def load() -> C.CDLL:
     sig("ldagpu_get_abort", C.c_int, vp, pi32)
     sig("ldagpu_get_timers", C.c_int, vp, pf64, pf64, pf64, pf64)
     sig("ldagpu_get_last_call_stats", C.c_int, vp, pf64, pf64, pi64, pi64)
-    sig("ldagpu_synth_corpus", C.c_int, i64, i64, i32, i32, f64, f64, i32, u64, vp, vp, i64, pi64)
     _lib = L
     return L
 
@@ -87,18 +90,36 @@ def ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 
 
+SYNTH_SO_PATH = os.path.join(_HERE, "libldasynth.so")
+_synth = None
+
+
+def load_synth() -> C.CDLL:
+    """libldasynth.so (include/ldasynth.h): host-only corpus generator, separate from the product library."""
+    global _synth
+    if _synth is None:
+        if not os.path.exists(SYNTH_SO_PATH):
+            raise LdaGpuError(f"{SYNTH_SO_PATH} is missing: build it with `python -m ldagroupedgibbssampler_b200.build`")
+        S = C.CDLL(SYNTH_SO_PATH)
+        S.ldasynth_corpus.restype = C.c_int
+        S.ldasynth_corpus.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32,
+                                      C.c_uint64, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        _synth = S
+    return _synth
+
+
 def synth_corpus(D: int, V: int, mean_len: float, seed: int = 20190529, K_gen: int = 50,
                  sigma_len: float = 0.6, max_len: int = 20000, doc_first: int = 0):
     """LDA-generative synthetic corpus of a given shape.  Returns (doc_offsets, tokens)."""
-    L = load()
+    S = load_synth()
     off = np.zeros(D + 1, np.int64)
     n = C.c_int64(0)
-    rc = L.ldagpu_synth_corpus(D, doc_first, V, K_gen, mean_len, sigma_len, max_len, seed, ptr(off), None, 0, C.byref(n))
+    rc = S.ldasynth_corpus(D, doc_first, V, K_gen, mean_len, sigma_len, max_len, seed, ptr(off), None, 0, C.byref(n))
     if rc:
-        raise LdaGpuError("ldagpu_synth_corpus (sizing) failed")
+        raise LdaGpuError("ldasynth_corpus (sizing) failed")
     tokens = np.zeros(max(n.value, 1), np.int32)
-    rc = L.ldagpu_synth_corpus(D, doc_first, V, K_gen, mean_len, sigma_len, max_len, seed, ptr(off), ptr(tokens),
-                               n.value, C.byref(n))
+    rc = S.ldasynth_corpus(D, doc_first, V, K_gen, mean_len, sigma_len, max_len, seed, ptr(off), ptr(tokens),
+                           n.value, C.byref(n))
     if rc:
-        raise LdaGpuError("ldagpu_synth_corpus failed")
+        raise LdaGpuError("ldasynth_corpus failed")
     return off, tokens[: n.value]

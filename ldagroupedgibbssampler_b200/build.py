@@ -20,7 +20,8 @@ OBJ = os.path.join(HERE, "_obj")
 OUT = os.path.join(HERE, "libldagpu.so")
 
 CU = ["kernels_z.cu", "kernels_z_big.cu", "kernels_sparse.cu", "kernels_phi.cu", "kernels_p2p.cu", "kernels_misc.cu", "engine.cu"]
-CPP = ["synth.cpp"]
+CPP = []
+SYNTH_SRC, SYNTH_OUT = os.path.join(CSRC, "synth.cpp"), os.path.join(HERE, "libldasynth.so")
 HEADERS = ["common.cuh", "contract_math.cuh", os.path.join("..", "..", "include", "ldagpu.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -68,7 +69,16 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
+    build_synth(force)
     return out
+
+
+def build_synth(force: bool = False) -> str:
+    """libldasynth.so: the synthetic-corpus generator, host C++ only (no CUDA), its own library."""
+    hdr = os.path.normpath(os.path.join(CSRC, "..", "..", "include", "ldasynth.h"))
+    if force or _newer(SYNTH_SRC, SYNTH_OUT) or _newer(hdr, SYNTH_OUT):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", SYNTH_SRC, "-o", SYNTH_OUT])
+    return SYNTH_OUT
 
 
 if __name__ == "__main__":

@@ -3,6 +3,12 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "contract_math.cuh"
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
 namespace ldagpu {
 
 constexpr int TILE = 128;            // topics per warp tile: lane l owns topics 4l..4l+3 of the tile
@@ -16,8 +22,9 @@ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 struct Dims {
     int32_t K;        // topics
-    int32_t Ks;       // row stride of Phi^T / n_wk / theta in elements: round_up(K, 32)
-    int32_t NT;       // tiles: ceil(K / 128)
+    int32_t Ks;       // row stride of Phi^T / n_wk / theta in elements: 128 * NT on the register path, else round_up(K, 32)
+    int32_t NT;       // tiles of a row: 1, 2, 4 or 8 for K <= 1024 (register path), ceil(K / 128) above
+    int32_t lg;       // log2 of the topics one lane owns on the register path (2 = rows in natural topic order)
     int32_t V;        // vocabulary
     int32_t Vp;       // padded vocabulary rows: round_up(V, 64)
     int64_t D;        // local documents
@@ -26,21 +33,40 @@ struct Dims {
     int64_t token_base;  // global index of local token 0
 };
 
+// Row layout.  On the register path (K <= 1024) lane l of a warp owns the L = 4 * NT
+// CONSECUTIVE topics [l * L, (l + 1) * L) (contract 4.2), but reads them as one coalesced float4 per tile: a
+// row of Phi^T / n_wk / theta stores topic k = l * L + 4 * j + i at column 128 * j + 4 * l + i -- a
+// permutation of the bits of k.  Topic indicators (z), alpha and n_k stay in natural topic order; every
+// kernel that indexes a row by topic goes through these two functions.  lg == 2 is the identity
+// (K <= 128, the K > 1024 path and the sparse scheme).
+__host__ __device__ __forceinline__ int tpos_lg(int lg, int k)
+{
+    return (((k & ((1 << lg) - 1)) >> 2) << 7) | ((k >> lg) << 2) | (k & 3);
+}
+__host__ __device__ __forceinline__ int ttopic_lg(int lg, int p)
+{
+    return lg == 2 ? p : ((((p >> 2) & 31) << lg) | ((p >> 7) << 2) | (p & 3));
+}
+__host__ __device__ __forceinline__ int tpos(const Dims &dm, int k) { return tpos_lg(dm.lg, k); }      // topic -> column
+__host__ __device__ __forceinline__ int ttopic(const Dims &dm, int p) { return ttopic_lg(dm.lg, p); }  // column -> topic
+
 struct ZArgs {
     Dims dm;
     const int64_t *doc_off;   // [D+1] local CSR
     const int32_t *tokens;    // [N]
     int32_t *z;               // [N] in/out
     const float *phiT;        // [Vp][Ks]
-    const float *theta;       // [D][Ks] (GGS)
-    const float *alpha;       // [Ks]   (PCGS)
+    float *theta;             // [D][Ks] (GGS): read for chunks of long documents, written when the warp draws it
+    const float *alpha;       // [Ks], natural topic order
     const int32_t *item_doc;  // GGS: [n_items] document of each chunk; PCGS: [D] LPT order
     const int64_t *item_begin;// GGS: [n_items] first token of each chunk
     int64_t n_items;
     int32_t chunk;            // GGS: tokens per work item
+    int32_t fuse_theta;       // GGS: a work item that covers a whole document draws its theta itself
     unsigned long long *work_counter;
     int32_t *n_wk_out;        // when set (zeroed by the caller), the z-step also adds the new (w, z) counts
     uint32_t seed_lo, seed_hi, sweep;
+    PhiloxKeys rk;            // round keys of (seed_lo, seed_hi)
 };
 
 struct ThetaArgs {
@@ -49,8 +75,11 @@ struct ThetaArgs {
     const int32_t *z;
     const float *alpha;   // [Ks]
     float *theta;         // [D][Ks]
+    const int32_t *doc_list;  // documents to draw (n_docs entries), or null = all D documents
+    int64_t n_docs;
     unsigned long long *work_counter;
     uint32_t seed_lo, seed_hi, sweep;
+    PhiloxKeys rk;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -92,6 +121,33 @@ cudaError_t launch_phi_normalise_p2p(const PeerTable &pt, uint32_t epoch_seg, ui
                                      double *topic_sum, double *phi_mean_sum, int32_t row0, int32_t row1,
                                      cudaStream_t st);
 
+// Opt a kernel into `smem` bytes of dynamic shared memory and report how many CTAs of `threads` threads fit
+// one SM.  Both are properties of the CURRENT DEVICE, so the cache is keyed by the device ordinal (a second
+// handle on another GPU of the same process gets its own opt-in) and guarded by a mutex.
+inline cudaError_t kernel_config(const void *func, int threads, size_t smem, int *ctas_per_sm)
+{
+    static std::mutex mu;
+    static std::map<std::tuple<const void *, int, int, size_t>, int> cache;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    const auto key = std::make_tuple(func, dev, threads, smem);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        if (smem > 48 * 1024) {   // below that no opt-in is needed
+            e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        int n = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, func, threads, smem);
+        if (e != cudaSuccess) return e;
+        it = cache.emplace(key, n < 1 ? 1 : n).first;
+    }
+    if (ctas_per_sm) *ctas_per_sm = it->second;
+    return cudaSuccess;
+}
+
 // launchers (each returns the cudaError of the launch)
 cudaError_t launch_theta(const ThetaArgs &a, int sm_count, cudaStream_t st);
 cudaError_t launch_z_ggs(const ZArgs &a, int sm_count, cudaStream_t st);
@@ -120,6 +176,8 @@ cudaError_t launch_counts(const Dims &dm, const int32_t *tokens, const int32_t *
                           int32_t *n_k, int sm_count, cudaStream_t st);
 cudaError_t launch_counts_chunk(const Dims &dm, const int32_t *tokens, const int32_t *z, int64_t n, int32_t *n_wk,
                                 int *bad, int sm_count, cudaStream_t st);
+cudaError_t launch_unpack16(const uint16_t *in, int32_t *out, int64_t n, int sm_count, cudaStream_t st);
+cudaError_t launch_pack16(const int32_t *in, uint16_t *out, int64_t n, int sm_count, cudaStream_t st);
 cudaError_t launch_topic_totals(const Dims &dm, const int32_t *n_wk, int32_t *n_k, cudaStream_t st);
 cudaError_t launch_doc_topic_counts(const Dims &dm, const int64_t *doc_off, const int32_t *z,
                                     int32_t *n_dk /*[D][K] dense*/, cudaStream_t st);

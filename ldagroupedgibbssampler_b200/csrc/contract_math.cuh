@@ -36,6 +36,34 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     return make_uint4(c0, c1, c2, c3);
 }
 
+// The same generator with the ten round keys (k + r * Weyl constant) formed once on the host and passed as a
+// kernel argument: they reach the xor as constant-bank operands, and each 32x32 product is ONE wide multiply --
+// about half the instructions of the version above, bit-identical output.
+struct PhiloxKeys {
+    uint32_t k0[10], k1[10];
+};
+__host__ __device__ inline PhiloxKeys philox_keys(uint32_t k0, uint32_t k1)
+{
+    PhiloxKeys r;
+    for (int i = 0; i < 10; ++i) {
+        r.k0[i] = k0 + 0x9E3779B9u * (uint32_t)i;
+        r.k1[i] = k1 + 0xBB67AE85u * (uint32_t)i;
+    }
+    return r;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys &rk)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+        const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk.k0[r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ rk.k1[r];
+        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
 // open-interval uniform from the top 23 bits: (n + 1/2) 2^-23, exact in fp32
 __device__ __forceinline__ float uniform23(uint32_t w)
 {

@@ -128,7 +128,9 @@ struct ldagpu_handle_s {
     int64_t D_global = 0;
 
     DevBuf<int64_t> doc_off, item_begin;
-    DevBuf<int32_t> tokens, z, n_wk, n_k, item_doc, scratch_i32;
+    DevBuf<int32_t> tokens, z, z_stage, n_wk, n_k, item_doc, long_docs, scratch_i32;
+    DevBuf<uint16_t> z16;   // 16-bit transport buffer of the topic indicators (ldagpu_set_z16 / ldagpu_sweep_get_z16)
+    int64_t n_long_docs = 0;   // GGS: documents longer than one work item (their theta is drawn before the z-step)
     DevBuf<float> phiT, theta, alpha_f;
     // sparse scheme: per-type alias tables over alpha_k * phi_kw and the build scratch
     DevBuf<float> type_norm;
@@ -219,21 +221,28 @@ int ensure_theta(ldagpu_handle h)
     return 0;
 }
 
-int step_theta(ldagpu_handle h)
+// theta_d ~ Dir(n_d + alpha) for every document, or (only_long, inside a sweep) for the documents that the
+// z-step splits into several work items -- the others draw their theta inside the z kernel
+int step_theta(ldagpu_handle h, bool only_long = false)
 {
     if (ensure_theta(h)) return 1;
+    const bool fused_path = h->dm.K <= MAX_REG_TILES * TILE;
+    if (only_long && fused_path && h->n_long_docs == 0) return 0;
     CK(h, cudaMemsetAsync(h->counter.p, 0, sizeof(unsigned long long), h->stream));
     ThetaArgs a{};
     a.dm = h->dm; a.doc_off = h->doc_off.p; a.z = h->z.p; a.alpha = h->alpha_f.p; a.theta = h->theta.p;
+    a.doc_list = nullptr; a.n_docs = h->dm.D;
+    if (only_long && fused_path) { a.doc_list = h->long_docs.p; a.n_docs = h->n_long_docs; }
     a.work_counter = h->counter.p;
     a.seed_lo = (uint32_t)h->seed; a.seed_hi = (uint32_t)(h->seed >> 32); a.sweep = (uint32_t)h->iteration;
+    a.rk = philox_keys(a.seed_lo, a.seed_hi);
     CK(h, launch_theta(a, h->sm_count, h->stream));
     h->last_launches += 1;
     return 0;
 }
 
 // fused: the z kernel also accumulates n_wk (which the caller has zeroed)
-int step_z(ldagpu_handle h, bool fused = false)
+int step_z(ldagpu_handle h, bool fused = false, bool fuse_theta = false)
 {
     CK(h, cudaMemsetAsync(h->counter.p, 0, sizeof(unsigned long long), h->stream));
     ZArgs a{};
@@ -241,7 +250,9 @@ int step_z(ldagpu_handle h, bool fused = false)
     a.theta = h->theta.p; a.alpha = h->alpha_f.p; a.item_doc = h->item_doc.p; a.item_begin = h->item_begin.p;
     a.n_items = h->n_items; a.chunk = h->ggs_chunk; a.work_counter = h->counter.p;
     a.n_wk_out = fused ? h->n_wk.p : nullptr;
+    a.fuse_theta = fuse_theta ? 1 : 0;
     a.seed_lo = (uint32_t)h->seed; a.seed_hi = (uint32_t)(h->seed >> 32); a.sweep = (uint32_t)h->iteration;
+    a.rk = philox_keys(a.seed_lo, a.seed_hi);
     if (h->scheme == LDAGPU_SCHEME_GGS) {
         if (!h->theta.p) return h->fail("GGS z-step needs theta: call ldagpu_sample_theta or ldagpu_set_theta first");
         CK(h, launch_z_ggs(a, h->sm_count, h->stream));
@@ -397,7 +408,7 @@ int sync_check(ldagpu_handle h)
 // z_out != nullptr: the topic indicators of the last sweep are copied to the host on the copy stream as soon as
 // its z-step has finished, under the count exchange and the Phi draw (the Java shim copies z back into the
 // documents' LabelSequences after every sample() call)
-int run_sweeps(ldagpu_handle h, int32_t n, bool with_phi, int32_t *done, int32_t *z_out = nullptr)
+int run_sweeps(ldagpu_handle h, int32_t n, bool with_phi, int32_t *done, int32_t *z_out = nullptr, uint16_t *z16_out = nullptr)
 {
     h->last_zk_ms = 0; h->last_call_ms = 0; h->last_zk_launches = 0; h->last_launches = 0;
     if (done) *done = 0;
@@ -413,14 +424,23 @@ int run_sweeps(ldagpu_handle h, int32_t n, bool with_phi, int32_t *done, int32_t
         CK(h, cudaEventRecord(ev[0], h->stream));
         // the count rebuild is fused into the z kernel: zero n_wk first (Phi, not n_wk, feeds the z-step)
         CK(h, cudaMemsetAsync(h->n_wk.p, 0, sizeof(int32_t) * h->n_wk.n, h->stream));
-        if (h->scheme == LDAGPU_SCHEME_GGS && step_theta(h)) return 1;
+        // LDAGPU_FUSE_THETA=0 (tuning knob): theta for all documents up front, as round 1 did
+        static const bool fuse_env = !(getenv("LDAGPU_FUSE_THETA") && atoi(getenv("LDAGPU_FUSE_THETA")) == 0);
+        const bool fuse_theta = h->scheme == LDAGPU_SCHEME_GGS && fuse_env;
+        if (h->scheme == LDAGPU_SCHEME_GGS && step_theta(h, fuse_theta)) return 1;
         CK(h, cudaEventRecord(ev[1], h->stream));
-        if (step_z(h, true)) return 1;
+        if (step_z(h, true, fuse_theta)) return 1;
         CK(h, cudaEventRecord(ev[2], h->stream));
-        if (z_out && s == n - 1 && h->dm.N) {
+        if ((z_out || z16_out) && s == n - 1 && h->dm.N) {
             CK(h, cudaEventRecord(h->copy_events[0], h->stream));
             CK(h, cudaStreamWaitEvent(h->copy_stream, h->copy_events[0], 0));
-            CK(h, cudaMemcpyAsync(z_out, h->z.p, sizeof(int32_t) * (size_t)h->dm.N, cudaMemcpyDeviceToHost, h->copy_stream));
+            if (z16_out) {   // narrow on the device (copy stream, under the Phi draw), half the PCIe bytes
+                CK(h, launch_pack16(h->z.p, h->z16.p, h->dm.N, h->sm_count, h->copy_stream));
+                CK(h, cudaMemcpyAsync(z16_out, h->z16.p, sizeof(uint16_t) * (size_t)h->dm.N, cudaMemcpyDeviceToHost, h->copy_stream));
+                h->last_launches += 1;
+            } else {
+                CK(h, cudaMemcpyAsync(z_out, h->z.p, sizeof(int32_t) * (size_t)h->dm.N, cudaMemcpyDeviceToHost, h->copy_stream));
+            }
             z_copied = true;
         }
         CK(h, launch_topic_totals(h->dm, h->n_wk.p, h->n_k.p, h->stream));
@@ -437,8 +457,13 @@ int run_sweeps(ldagpu_handle h, int32_t n, bool with_phi, int32_t *done, int32_t
         }
         ++ran;
     }
-    if (z_out && !z_copied && h->dm.N)   // aborted before the last sweep (or n == 0): plain copy of the current z
-        CK(h, cudaMemcpyAsync(z_out, h->z.p, sizeof(int32_t) * (size_t)h->dm.N, cudaMemcpyDeviceToHost, h->stream));
+    if (!z_copied && h->dm.N) {   // aborted before the last sweep: plain copy of the current z
+        if (z_out) CK(h, cudaMemcpyAsync(z_out, h->z.p, sizeof(int32_t) * (size_t)h->dm.N, cudaMemcpyDeviceToHost, h->stream));
+        if (z16_out) {
+            CK(h, launch_pack16(h->z.p, h->z16.p, h->dm.N, h->sm_count, h->stream));
+            CK(h, cudaMemcpyAsync(z16_out, h->z16.p, sizeof(uint16_t) * (size_t)h->dm.N, cudaMemcpyDeviceToHost, h->stream));
+        }
+    }
     if (sync_check(h)) return 1;
     if (z_copied) CK(h, cudaStreamSynchronize(h->copy_stream));
     for (int32_t s = 0; s < ran; ++s) {
@@ -480,11 +505,18 @@ int build_items(ldagpu_handle h)
         int64_t chunk = (h->dm.N / (8 * resident_warps) + 31) / 32 * 32;
         chunk = std::min<int64_t>(std::max<int64_t>(chunk, 32), GGS_CHUNK_MAX);
         h->ggs_chunk = (int32_t)chunk;
-        for (int64_t d = 0; d < D; ++d)
+        std::vector<int32_t> long_docs;
+        for (int64_t d = 0; d < D; ++d) {
+            if (off[d + 1] - off[d] > chunk) long_docs.push_back((int32_t)d);
             for (int64_t t = off[d]; t < off[d + 1]; t += chunk) {
                 item_doc.push_back((int32_t)d);
                 item_begin.push_back(t);
             }
+        }
+        h->n_long_docs = (int64_t)long_docs.size();
+        CK(h, h->long_docs.alloc(std::max<size_t>(long_docs.size(), 1)));
+        if (!long_docs.empty())
+            CK(h, cudaMemcpy(h->long_docs.p, long_docs.data(), sizeof(int32_t) * long_docs.size(), cudaMemcpyHostToDevice));
     } else {
         // PCGS is sequential inside a document: one item per document, longest first
         item_doc.resize((size_t)D);
@@ -663,7 +695,14 @@ int ldagpu_create(int32_t K, int32_t V, int64_t D, const int64_t *doc_offsets, c
     h->alpha_sum = 0.0;
     for (int k = 0; k < K; ++k) h->alpha_sum += alpha[k];   // sequential, as MSL:139-143
     Dims &dm = h->dm;
-    dm.K = K; dm.Ks = (int32_t)round_up(K, 32); dm.NT = (K + TILE - 1) / TILE;
+    dm.K = K; dm.Ks = (int32_t)round_up(K, 32); dm.NT = (K + TILE - 1) / TILE; dm.lg = 2;
+    if (scheme != LDAGPU_SCHEME_SPALIAS && K <= MAX_REG_TILES * TILE) {
+        // register path of the dense z-step: 1, 2, 4 or 8 tiles, lane l owns 4 * NT consecutive topics and the
+        // rows of Phi^T / n_wk / theta are stored in the matching column order (common.cuh: tpos / ttopic)
+        dm.NT = K <= 128 ? 1 : K <= 256 ? 2 : K <= 512 ? 4 : 8;
+        dm.Ks = dm.NT * TILE;
+        dm.lg = dm.NT == 1 ? 2 : dm.NT == 2 ? 3 : dm.NT == 4 ? 4 : 5;
+    }
     dm.V = V; dm.Vp = (int32_t)round_up(V, PHI_ROW_BLOCK * PHI_SEGMENTS);
     dm.D = D; dm.N = doc_offsets[D]; dm.doc_base = doc_base; dm.token_base = token_base;
     h->D_global = D;
@@ -764,8 +803,9 @@ int ldagpu_destroy(ldagpu_handle h)
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
     for (cudaEvent_t e : h->copy_events) cudaEventDestroy(e);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
-    h->doc_off.release(); h->item_begin.release(); h->tokens.release(); h->z.release(); h->n_wk.release();
-    h->n_k.release(); h->item_doc.release(); h->scratch_i32.release(); h->phiT.release(); h->theta.release();
+    h->doc_off.release(); h->item_begin.release(); h->tokens.release(); h->z.release(); h->z_stage.release(); h->z16.release();
+    h->n_wk.release();
+    h->n_k.release(); h->item_doc.release(); h->long_docs.release(); h->scratch_i32.release(); h->phiT.release(); h->theta.release();
     h->alpha_f.release(); h->alpha_d.release(); h->lgs_alpha.release(); h->partial.release(); h->seg.release(); h->topic_sum.release();
     h->phi_mean.release(); h->red.release(); h->red_out.release(); h->scratch_f64.release();
     h->counter.release(); h->bad.release();
@@ -845,40 +885,98 @@ int ldagpu_init_z_java_random(ldagpu_handle h, int32_t seed)
     return refresh_counts_and_phi(h, true);   // initialSamplePhi, UPL:450
 }
 
-int ldagpu_set_z(ldagpu_handle h, const int32_t *z, int32_t redraw_phi)
+// setZIndicators: the upload and the count rebuild are pipelined chunk by chunk -- the copy stream brings z in,
+// the main stream checks the range and accumulates n_wk for the chunk that has landed (UPL:1797-1830 rebuilds
+// while it copies too).  The new indicators land in a STAGING buffer and only replace the resident z once every
+// one of them is inside [0, K): on an out-of-range indicator the reference throws and keeps its state
+// (UPL:475-481), so do we -- the counts are rebuilt from the untouched z and the call fails.
+// is16: the host buffer holds uint16 (half the PCIe bytes); it is widened on the device.
+static int set_z_impl(ldagpu_handle h, const void *z, bool is16, int32_t redraw_phi)
 {
-    NEED(h);
     const int64_t N = h->dm.N;
     if (!z && N) return h->fail("null z");
-    // upload and count rebuild pipelined chunk by chunk: the copy stream brings z in, the main stream checks
-    // the range and accumulates n_wk for the chunk that has landed (UPL:1797-1830 rebuilds while it copies too)
+    if (is16 && h->dm.K > 65536) return h->fail("16-bit topic indicators need K <= 65536");
+    const size_t N1 = (size_t)std::max<int64_t>(N, 1);
+    if (!h->z_stage.p) {
+        CK(h, h->z_stage.alloc(N1 + 4));
+        CK(h, cudaMemsetAsync(h->z_stage.p, 0, sizeof(int32_t) * h->z_stage.n, h->stream));
+    }
+    if (is16 && !h->z16.p) CK(h, h->z16.alloc(N1 + 8));
     CK(h, cudaMemsetAsync(h->n_wk.p, 0, sizeof(int32_t) * h->n_wk.n, h->stream));
     CK(h, cudaMemsetAsync(h->bad.p, 0, sizeof(int), h->stream));
     CK(h, cudaEventRecord(h->copy_events[0], h->stream));
-    CK(h, cudaStreamWaitEvent(h->copy_stream, h->copy_events[0], 0));   // earlier readers of z are done
+    CK(h, cudaStreamWaitEvent(h->copy_stream, h->copy_events[0], 0));   // earlier users of the staging buffers are done
     const int nchunk = N >= (8 << 20) ? 8 : 1;
-    const int64_t per = ((N + nchunk - 1) / nchunk + 3) / 4 * 4;        // int4 loads: chunks start on 16-byte boundaries
+    const int64_t per = ((N + nchunk - 1) / nchunk + 7) / 8 * 8;        // vector loads: chunks start on 16-byte boundaries
+    const size_t esz = is16 ? sizeof(uint16_t) : sizeof(int32_t);
     for (int c = 0; c < nchunk; ++c) {
         const int64_t o = (int64_t)c * per, cnt = std::min<int64_t>(per, N - o);
         if (cnt <= 0) break;
-        CK(h, cudaMemcpyAsync(h->z.p + o, z + o, sizeof(int32_t) * (size_t)cnt, cudaMemcpyHostToDevice, h->copy_stream));
+        void *dst = is16 ? static_cast<void *>(h->z16.p + o) : static_cast<void *>(h->z_stage.p + o);
+        CK(h, cudaMemcpyAsync(dst, static_cast<const char *>(z) + (size_t)o * esz, esz * (size_t)cnt, cudaMemcpyHostToDevice,
+                              h->copy_stream));
         CK(h, cudaEventRecord(h->copy_events[1 + c], h->copy_stream));
         CK(h, cudaStreamWaitEvent(h->stream, h->copy_events[1 + c], 0));
-        CK(h, launch_counts_chunk(h->dm, h->tokens.p + o, h->z.p + o, cnt, h->n_wk.p, h->bad.p, h->sm_count, h->stream));
+        if (is16) {
+            CK(h, launch_unpack16(h->z16.p + o, h->z_stage.p + o, cnt, h->sm_count, h->stream));
+            h->last_launches += 1;
+        }
+        CK(h, launch_counts_chunk(h->dm, h->tokens.p + o, h->z_stage.p + o, cnt, h->n_wk.p, h->bad.p, h->sm_count, h->stream));
     }
-    CK(h, launch_topic_totals(h->dm, h->n_wk.p, h->n_k.p, h->stream));
-    h->last_launches += nchunk + 1;
+    h->last_launches += nchunk;
     // sharded: every rank must take the same exit, or the others would wait for this one in the exchange
-    if (h->world > 1) NK(h, g_nccl.AllReduce(h->bad.p, h->bad.p, 1, ncclInt32, ncclMax, h->comm, h->stream));
+    if (h->world > 1 && h->comm) NK(h, g_nccl.AllReduce(h->bad.p, h->bad.p, 1, ncclInt32, ncclMax, h->comm, h->stream));
     int bad = 0;
     CK(h, cudaMemcpyAsync(&bad, h->bad.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
-    if (bad) return h->fail("topic indicator out of range [0, %d)%s", h->dm.K,   // UPL:475-481 throws
-                            h->world > 1 ? " (on this or another rank)" : "");
+    if (!bad) std::swap(h->z.p, h->z_stage.p);   // commit (both buffers have the same size)
+    else CK(h, cudaMemsetAsync(h->n_wk.p, 0, sizeof(int32_t) * h->n_wk.n, h->stream));
+    if (bad) {
+        // keep the previous state: counts from the untouched z, exchanged like any rebuild; Phi was never touched
+        if (rendezvous(h)) return 1;
+        if (step_counts_local(h) || step_counts_exchange(h, false)) return 1;
+        if (sync_check(h)) return 1;
+        return h->fail("topic indicator out of range [0, %d)%s; the previous indicators stay in place", h->dm.K,   // UPL:475-481 throws
+                       h->world > 1 ? " (on this or another rank)" : "");
+    }
+    CK(h, launch_topic_totals(h->dm, h->n_wk.p, h->n_k.p, h->stream));
+    h->last_launches += 1;
     if (rendezvous(h)) return 1;
     if (step_counts_exchange(h, redraw_phi != 0)) return 1;
     if (redraw_phi && step_phi(h, false, nullptr, true)) return 1;   // UPL:1842
     return sync_check(h);
+}
+
+int ldagpu_set_z(ldagpu_handle h, const int32_t *z, int32_t redraw_phi)
+{
+    NEED(h);
+    return set_z_impl(h, z, false, redraw_phi);
+}
+
+int ldagpu_set_z16(ldagpu_handle h, const uint16_t *z, int32_t redraw_phi)
+{
+    NEED(h);
+    return set_z_impl(h, z, true, redraw_phi);
+}
+
+int ldagpu_get_z16(ldagpu_handle h, uint16_t *z)
+{
+    NEED(h);
+    if (h->dm.K > 65536) return h->fail("16-bit topic indicators need K <= 65536");
+    if (!h->dm.N) return 0;
+    if (!h->z16.p) CK(h, h->z16.alloc((size_t)h->dm.N + 8));
+    CK(h, launch_pack16(h->z.p, h->z16.p, h->dm.N, h->sm_count, h->stream));
+    CK(h, cudaMemcpyAsync(z, h->z16.p, sizeof(uint16_t) * (size_t)h->dm.N, cudaMemcpyDeviceToHost, h->stream));
+    return sync_check(h);
+}
+
+int ldagpu_sweep_get_z16(ldagpu_handle h, int32_t n, int32_t *done, uint16_t *z)
+{
+    NEED(h);
+    if (!z && h->dm.N) return h->fail("null z");
+    if (h->dm.K > 65536) return h->fail("16-bit topic indicators need K <= 65536");
+    if (h->dm.N && !h->z16.p) CK(h, h->z16.alloc((size_t)h->dm.N + 8));
+    return run_sweeps(h, n, true, done, nullptr, z);
 }
 
 int ldagpu_sweep_get_z(ldagpu_handle h, int32_t n, int32_t *done, int32_t *z)

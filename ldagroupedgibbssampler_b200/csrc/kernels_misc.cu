@@ -41,7 +41,7 @@ counts_kernel(Dims dm, const int32_t *__restrict__ tokens, const int32_t *__rest
         const int ww[4] = {w4.x, w4.y, w4.z, w4.w};
         const int zz[4] = {z4.x, z4.y, z4.z, z4.w};
 #pragma unroll
-        for (int s = 0; s < 4; ++s) key[s] = (size_t)ww[s] * (size_t)dm.Ks + (size_t)zz[s];
+        for (int s = 0; s < 4; ++s) key[s] = (size_t)ww[s] * (size_t)dm.Ks + (size_t)tpos(dm, zz[s]);
         if (CHECK) {
 #pragma unroll
             for (int s = 0; s < 4; ++s)
@@ -58,7 +58,7 @@ counts_kernel(Dims dm, const int32_t *__restrict__ tokens, const int32_t *__rest
     if (blockIdx.x == 0)
         for (int64_t i = n4 * 4 + threadIdx.x; i < dm.N; i += blockDim.x) {
             if (CHECK && (unsigned)z[i] >= (unsigned)dm.K) { atomicOr(bad, 2); continue; }
-            atomicAdd(&n_wk[(size_t)tokens[i] * dm.Ks + z[i]], 1);
+            atomicAdd(&n_wk[(size_t)tokens[i] * dm.Ks + tpos(dm, z[i])], 1);
         }
 }
 
@@ -88,8 +88,9 @@ topic_totals_kernel(Dims dm, const int32_t *__restrict__ n_wk, int32_t *__restri
     int acc = 0;
     const int rows = (dm.V + gridDim.y - 1) / gridDim.y;
     const int w0 = blockIdx.y * rows, w1 = min(w0 + rows, dm.V);
+    const int col = tpos(dm, k);   // n_k is in natural topic order, the rows are not (common.cuh)
 #pragma unroll 8
-    for (int w = w0; w < w1; ++w) acc += n_wk[(size_t)w * dm.Ks + k];
+    for (int w = w0; w < w1; ++w) acc += n_wk[(size_t)w * dm.Ks + col];
     if (acc) atomicAdd(&n_k[k], acc);
 }
 
@@ -141,6 +142,48 @@ cudaError_t launch_doc_topic_counts(const Dims &dm, const int64_t *doc_off, cons
     int64_t grid = (dm.D + 7) / 8;
     if (grid > 65535 * 16) grid = 65535 * 16;
     doc_topic_kernel<<<(unsigned)grid, 256, 0, st>>>(dm, doc_off, z, n_dk);
+    return cudaGetLastError();
+}
+
+// 16-bit transport of the topic indicators over PCIe (K <= 65 536): ldagpu_set_z16 / ldagpu_get_z16 /
+// ldagpu_sweep_get_z16 move uint16 and convert on the device; the device copy stays int32
+__global__ void unpack16_kernel(const uint16_t *__restrict__ in, int32_t *__restrict__ out, int64_t n)
+{
+    const int64_t n4 = n / 4, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const ushort4 v = __ldg(reinterpret_cast<const ushort4 *>(in) + i);
+        reinterpret_cast<int4 *>(out)[i] = make_int4(v.x, v.y, v.z, v.w);
+    }
+    if (blockIdx.x == 0)
+        for (int64_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) out[i] = in[i];
+}
+__global__ void pack16_kernel(const int32_t *__restrict__ in, uint16_t *__restrict__ out, int64_t n)
+{
+    const int64_t n4 = n / 4, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int4 v = __ldg(reinterpret_cast<const int4 *>(in) + i);
+        reinterpret_cast<ushort4 *>(out)[i] = make_ushort4((unsigned short)v.x, (unsigned short)v.y, (unsigned short)v.z,
+                                                           (unsigned short)v.w);
+    }
+    if (blockIdx.x == 0)
+        for (int64_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) out[i] = (uint16_t)in[i];
+}
+static unsigned copy_grid(int64_t n, int sm_count)
+{
+    int64_t need = (n / 4 + 255) / 256, grid = (int64_t)sm_count * 8;
+    if (need < grid) grid = need;
+    return (unsigned)(grid < 1 ? 1 : grid);
+}
+cudaError_t launch_unpack16(const uint16_t *in, int32_t *out, int64_t n, int sm_count, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    unpack16_kernel<<<copy_grid(n, sm_count), 256, 0, st>>>(in, out, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_pack16(const int32_t *in, uint16_t *out, int64_t n, int sm_count, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    pack16_kernel<<<copy_grid(n, sm_count), 256, 0, st>>>(in, out, n);
     return cudaGetLastError();
 }
 
@@ -256,12 +299,8 @@ cudaError_t launch_ll_doc(const Dims &dm, const int64_t *doc_off, const int32_t 
     int warps = RED_THREADS / 32;
     while (warps > 1 && sizeof(int32_t) * (size_t)dm.Ks * warps > 200 * 1024) warps /= 2;
     size_t smem = sizeof(int32_t) * (size_t)dm.Ks * warps;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(ll_doc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    cudaError_t e = kernel_config(reinterpret_cast<const void *>(ll_doc_kernel), warps * 32, smem, nullptr);
+    if (e != cudaSuccess) return e;
     ll_doc_kernel<<<n_partials, warps * 32, smem, st>>>(dm, doc_off, z, alpha, lgs_alpha, alpha_sum, partials);
     return cudaGetLastError();
 }
@@ -275,8 +314,8 @@ ll_type_kernel(Dims dm, const int32_t *__restrict__ n_wk, double beta, int32_t r
     const int64_t cells = (int64_t)(row1 - row0) * dm.Ks;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (int64_t)gridDim.x * blockDim.x) {
         const int32_t w = row0 + (int32_t)(i / dm.Ks);
-        const int k = (int)(i % dm.Ks);
-        if (w >= dm.V || k >= dm.K) continue;
+        const int k = (int)(i % dm.Ks);   // column; padding columns belong to no topic
+        if (w >= dm.V || ttopic(dm, k) >= dm.K) continue;
         int c = n_wk[(size_t)w * dm.Ks + k];
         if (c > 0) { acc += lgamma_stirling(beta + (double)c); nnz += 1.0; }
     }
@@ -317,7 +356,7 @@ lp_tokens_kernel(Dims dm, const int32_t *__restrict__ tokens, const int32_t *__r
 {
     double acc = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < dm.N; i += (int64_t)gridDim.x * blockDim.x)
-        acc += c_ln<double>((double)phiT[(size_t)tokens[i] * dm.Ks + z[i]] + 1e-12);
+        acc += c_ln<double>((double)phiT[(size_t)tokens[i] * dm.Ks + tpos(dm, z[i])] + 1e-12);
     double t = block_sum(acc);
     if (threadIdx.x == 0) partials[blockIdx.x] = t;
 }
@@ -343,7 +382,7 @@ lp_theta_kernel(Dims dm, const int64_t *__restrict__ doc_off, const int32_t *__r
         __syncwarp();
         const float *trow = theta + (size_t)d * dm.Ks;
         for (int k = lane; k < dm.K; k += 32) {
-            acc += ((double)cnt[k] + alpha[k] - 1.0) * c_ln<double>((double)trow[k] + 1e-12);
+            acc += ((double)cnt[k] + alpha[k] - 1.0) * c_ln<double>((double)trow[tpos(dm, k)] + 1e-12);
             cnt[k] = 0;
         }
         __syncwarp();
@@ -359,12 +398,8 @@ cudaError_t launch_lp_theta(const Dims &dm, const int64_t *doc_off, const int32_
     int warps = RED_THREADS / 32;
     while (warps > 1 && sizeof(int32_t) * (size_t)dm.Ks * warps > 200 * 1024) warps /= 2;
     size_t smem = sizeof(int32_t) * (size_t)dm.Ks * warps;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(lp_theta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    cudaError_t e = kernel_config(reinterpret_cast<const void *>(lp_theta_kernel), warps * 32, smem, nullptr);
+    if (e != cudaSuccess) return e;
     lp_theta_kernel<<<n_partials, warps * 32, smem, st>>>(dm, doc_off, z, theta, alpha, partials);
     return cudaGetLastError();
 }
@@ -378,7 +413,7 @@ lp_phi_kernel(Dims dm, const float *__restrict__ phiT, double beta, int32_t row0
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (int64_t)gridDim.x * blockDim.x) {
         const int32_t w = row0 + (int32_t)(i / dm.Ks);
         const int k = (int)(i % dm.Ks);
-        if (w >= dm.V || k >= dm.K) continue;
+        if (w >= dm.V || ttopic(dm, k) >= dm.K) continue;
         acc += c_ln<double>((double)phiT[(size_t)w * dm.Ks + k] + 1e-12);
     }
     double t = block_sum(acc);
@@ -401,7 +436,7 @@ __global__ void export_phi_kernel(Dims dm, const float *__restrict__ phiT, doubl
     const int w0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         int w = w0 + r, k = k0 + threadIdx.x;
-        tile[r][threadIdx.x] = (w < dm.V && k < dm.K) ? phiT[(size_t)w * dm.Ks + k] : 0.0f;
+        tile[r][threadIdx.x] = (w < dm.V && k < dm.K) ? phiT[(size_t)w * dm.Ks + tpos(dm, k)] : 0.0f;
     }
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -427,7 +462,7 @@ __global__ void import_phi_kernel(Dims dm, const double *__restrict__ in, float 
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         int w = w0 + r, k = k0 + threadIdx.x;
-        if (w < dm.V && k < dm.K) phiT[(size_t)w * dm.Ks + k] = tile[threadIdx.x][r];
+        if (w < dm.V && k < dm.K) phiT[(size_t)w * dm.Ks + tpos(dm, k)] = tile[threadIdx.x][r];
     }
 }
 cudaError_t launch_import_phi(const Dims &dm, const double *phi_kv, float *phiT, cudaStream_t st)
@@ -445,7 +480,7 @@ __global__ void export_mean_kernel(Dims dm, const double *__restrict__ sum_vk, d
     const int w0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         int w = w0 + r, k = k0 + threadIdx.x;
-        tile[r][threadIdx.x] = (w < dm.V && k < dm.K) ? sum_vk[(size_t)w * dm.Ks + k] : 0.0;
+        tile[r][threadIdx.x] = (w < dm.V && k < dm.K) ? sum_vk[(size_t)w * dm.Ks + tpos(dm, k)] : 0.0;
     }
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -464,7 +499,7 @@ __global__ void export_counts_kernel(Dims dm, const int32_t *__restrict__ n_wk, 
 {
     const int64_t cells = (int64_t)dm.V * dm.K;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (int64_t)gridDim.x * blockDim.x)
-        out[i] = n_wk[(size_t)(i / dm.K) * dm.Ks + (i % dm.K)];
+        out[i] = n_wk[(size_t)(i / dm.K) * dm.Ks + tpos(dm, (int)(i % dm.K))];
 }
 cudaError_t launch_export_counts(const Dims &dm, const int32_t *n_wk, int32_t *out_vk, cudaStream_t st)
 {
@@ -479,7 +514,7 @@ __global__ void export_theta_kernel(Dims dm, const float *__restrict__ theta, do
 {
     const int64_t cells = dm.D * dm.K;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (int64_t)gridDim.x * blockDim.x)
-        out[i] = (double)theta[(size_t)(i / dm.K) * dm.Ks + (i % dm.K)];
+        out[i] = (double)theta[(size_t)(i / dm.K) * dm.Ks + tpos(dm, (int)(i % dm.K))];
 }
 cudaError_t launch_export_theta(const Dims &dm, const float *theta, double *out, cudaStream_t st)
 {
@@ -495,7 +530,7 @@ __global__ void import_theta_kernel(Dims dm, const double *__restrict__ in, floa
     const int64_t cells = dm.D * dm.Ks;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t d = i / dm.Ks;
-        int k = (int)(i % dm.Ks);
+        const int k = ttopic(dm, (int)(i % dm.Ks));
         theta[i] = k < dm.K ? (float)in[(size_t)d * dm.K + k] : 0.0f;
     }
 }

@@ -50,7 +50,8 @@ phi_draw_kernel(PeerTable pt, uint32_t epoch_counts, Dims dm, int32_t *n_wk, int
     const int tid = threadIdx.x;
     // topic chunks vary fastest over the grid: the CTAs in flight together cover whole rows, so local and
     // peer accesses walk Phi^T / n_wk contiguously
-    const int k = blockIdx.x * PHI_THREADS + tid;
+    const int k = blockIdx.x * PHI_THREADS + tid;          // column of the rows (common.cuh: tpos / ttopic)
+    const int kt = ttopic(dm, k);                          // its topic: Philox counters and n_k are keyed by topic
     const int32_t wb = row0 + blockIdx.y * PHI_ROW_BLOCK;
     const bool col_ok = k < dm.Ks;
     if (tid == 0) { s_count = 0; s_next = PHI_THREADS; }
@@ -78,7 +79,7 @@ phi_draw_kernel(PeerTable pt, uint32_t epoch_counts, Dims dm, int32_t *n_wk, int
             s_g[r][tid] = 0.0f;
             if (col_ok && w < dm.V) n_wk[(size_t)w * dm.Ks + k] = acc[r];
         }
-        if (blockIdx.y == 0 && col_ok) {
+        if (blockIdx.y == 0 && k < dm.K) {
             const int32_t *parts = pt.nk_parts[pt.rank];
             int32_t t = 0;
             for (int q = 0; q < pt.world; ++q) t += __ldcg(parts + (size_t)q * dm.Ks + k);
@@ -99,14 +100,14 @@ phi_draw_kernel(PeerTable pt, uint32_t epoch_counts, Dims dm, int32_t *n_wk, int
     gamma_setup<double>(__dadd_rn(beta, 0.0), boost0, d0, c0, inva0);
     // ---- phase 1
     unsigned pend = 0;
-    if (k < dm.K) {
+    if (col_ok && kt < dm.K) {
 #pragma unroll 1
         for (int r = 0; r < PHI_ROW_BLOCK; ++r) {
             const int32_t w = wb + r;
             if (w >= dm.V) break;   // padding rows stay zero
             bool done = false;
             if (s_n[r][tid] == 0) {
-                const unsigned long long cell = (unsigned long long)w * (unsigned long long)dm.K + (unsigned long long)k;
+                const unsigned long long cell = (unsigned long long)w * (unsigned long long)dm.K + (unsigned long long)kt;
                 uint4 rnd = philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), sweep, STREAM_PHI << 24, seed_lo, seed_hi);
                 double g;
                 done = gamma_attempt_squeeze<double>(boost0, d0, c0, inva0, rnd, g);
@@ -131,7 +132,7 @@ phi_draw_kernel(PeerTable pt, uint32_t epoch_counts, Dims dm, int32_t *n_wk, int
         const int e = s_list[idx];
         const int r = e / PHI_THREADS, col = e % PHI_THREADS;
         const unsigned long long cell = (unsigned long long)(wb + r) * (unsigned long long)dm.K +
-                                        (unsigned long long)(blockIdx.x * PHI_THREADS + col);
+                                        (unsigned long long)ttopic(dm, blockIdx.x * PHI_THREADS + col);
         const double g = c_gamma<double>(__dadd_rn(beta, __int2double_rn(s_n[r][col])), seed_lo, seed_hi, cell,
                                          sweep, STREAM_PHI);
         s_g[r][col] = __double2float_rn(g);
@@ -247,8 +248,8 @@ phi_normalise_kernel(PeerTable pt, uint32_t epoch_seg, uint32_t epoch_phi, Dims 
         seg = pt.seg[pt.rank];
         phiT = pt.phiT[pt.rank];
     }
-    const int k = blockIdx.x * PHI_THREADS + threadIdx.x;   // topic chunks fastest (see phi_draw_kernel)
-    if (k < dm.K) {
+    const int k = blockIdx.x * PHI_THREADS + threadIdx.x;   // column; column chunks fastest (see phi_draw_kernel)
+    if (k < dm.Ks && ttopic(dm, k) < dm.K) {
         double s[PHI_SEGMENTS];
 #pragma unroll
         for (int i = 0; i < PHI_SEGMENTS; ++i) s[i] = P2P ? __ldcg(seg + (size_t)i * dm.Ks + k) : seg[(size_t)i * dm.Ks + k];
@@ -281,7 +282,7 @@ cudaError_t launch_phi_normalise(const Dims &dm, const double *seg, double *topi
 {
     for (int32_t r0 = row0; r0 < row1; r0 += MAX_GRID_Y * NORM_ROWS) {
         const int32_t r1 = r0 + MAX_GRID_Y * NORM_ROWS < row1 ? r0 + MAX_GRID_Y * NORM_ROWS : row1;
-        dim3 grid((dm.K + PHI_THREADS - 1) / PHI_THREADS, (r1 - r0 + NORM_ROWS - 1) / NORM_ROWS);
+        dim3 grid((dm.Ks + PHI_THREADS - 1) / PHI_THREADS, (r1 - r0 + NORM_ROWS - 1) / NORM_ROWS);
         phi_normalise_kernel<false><<<grid, PHI_THREADS, 0, st>>>(PeerTable{}, 0u, 0u, dm, seg, topic_sum, phiT,
                                                                   phi_mean_sum, r0, r1);
     }
@@ -294,7 +295,7 @@ cudaError_t launch_phi_normalise_p2p(const PeerTable &pt, uint32_t epoch_seg, ui
 {
     if (row1 <= row0) return cudaErrorInvalidValue;   // every rank owns rows
     if ((row1 - row0 + NORM_ROWS - 1) / NORM_ROWS > MAX_GRID_Y) return cudaErrorInvalidConfiguration;   // > 1M rows per rank
-    dim3 grid((dm.K + PHI_THREADS - 1) / PHI_THREADS, (row1 - row0 + NORM_ROWS - 1) / NORM_ROWS);
+    dim3 grid((dm.Ks + PHI_THREADS - 1) / PHI_THREADS, (row1 - row0 + NORM_ROWS - 1) / NORM_ROWS);
     phi_normalise_kernel<true><<<grid, PHI_THREADS, 0, st>>>(pt, epoch_seg, epoch_phi, dm, nullptr, topic_sum, nullptr,
                                                              phi_mean_sum, row0, row1);
     return cudaGetLastError();

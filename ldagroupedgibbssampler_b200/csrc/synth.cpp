@@ -1,4 +1,5 @@
-// synth.cpp -- host-side synthetic corpus generator for benchmarks and tests.
+// synth.cpp -- host-side synthetic corpus generator for benchmarks and tests; built into its own
+// libldasynth.so (g++ only), so users of it -- bench.py's reference arm, the CPU tests -- map no GPU code.
 //
 // LDA generative model with fixed seeds: Phi_true (K_gen x V) ~ Dir(0.01 * V * m) where m is a
 // Zipf(1.07) base measure over the vocabulary; per document a log-normal length clipped to
@@ -12,7 +13,7 @@
 #include <thread>
 #include <vector>
 
-#include "../../include/ldagpu.h"
+#include "../../include/ldasynth.h"
 
 namespace {
 
@@ -64,7 +65,7 @@ template <typename F> void parallel_for(int64_t n, F f)
 
 }  // namespace
 
-extern "C" int ldagpu_synth_corpus(int64_t D, int64_t doc_first, int32_t V, int32_t K_gen, double mean_len,
+extern "C" int ldasynth_corpus(int64_t D, int64_t doc_first, int32_t V, int32_t K_gen, double mean_len,
                                    double sigma_len, int32_t max_len, uint64_t seed, int64_t *doc_offsets,
                                    int32_t *tokens, int64_t capacity, int64_t *n_tokens)
 {

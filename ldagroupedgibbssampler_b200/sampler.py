@@ -233,16 +233,24 @@ class GpuLDASampler:
     def addTestInstances(self, testSet: InstanceList):
         raise NotImplementedError("held-out evaluation (MarginalProbEstimatorPlain) is outside the GPU path")
 
-    def sample(self, iterations: int, z_out: Optional[np.ndarray] = None):
+    SWEEPS_PER_CALL = 10   # the abort flag and the exec_time budget are looked at between library calls
+
+    def sample(self, iterations: int, z_out: Optional[np.ndarray] = None, chunk: Optional[int] = None):
         """UPL:552-943: `iterations` sweeps; log-likelihood every topic_interval sweeps when
-        compute_likelihood is set (UPL:587-593,838-853).  ``z_out`` (int32[N], ideally pinned): receives the
-        topic indicators after the last sweep, copied while that sweep's Phi draw still runs
-        (``ldagpu_sweep_get_z``) -- what the Java shim does after every sample() call."""
+        compute_likelihood is set (UPL:587-593,838-853).  ``z_out`` (int32[N] or uint16[N], ideally pinned):
+        receives the topic indicators after the last sweep, copied while that sweep's Phi draw still runs
+        (``ldagpu_sweep_get_z``) -- what the Java shim does after every sample() call.
+        The reference looks at ``abort`` and at ``zSamplingTimeCum + phiSamplingTimeCum >= exec_time`` after every
+        iteration (UPL:645,926-928).  Here at most ``chunk`` sweeps (default SWEEPS_PER_CALL) go into one library
+        call and both are checked between calls, with the timers counted from the start of THIS sample() call;
+        ``chunk=0`` puts everything into one call (benchmarks that time a fixed number of sweeps)."""
         self._need()
         cfg = self.config
         z_filled = False
-        if z_out is not None and (z_out.dtype != np.int32 or not z_out.flags.c_contiguous or z_out.size < len(self._tokens)):
-            raise ValueError("z_out must be a contiguous int32 array of at least N elements")
+        if z_out is not None and (z_out.dtype not in (np.int32, np.uint16) or not z_out.flags.c_contiguous
+                                  or z_out.size < len(self._tokens)):
+            raise ValueError("z_out must be a contiguous int32 (or uint16) array of at least N elements")
+        z16 = z_out is not None and z_out.dtype == np.uint16
         if cfg.save_phi_mean:
             burn = int(cfg.phi_mean_burnin / 100.0 * iterations)          # UPL:206-207
             self._ck(self._L.ldagpu_set_phi_mean_schedule(self._h, burn, cfg.phi_mean_thin))
@@ -251,10 +259,16 @@ class GpuLDASampler:
             self.loglikelihood.append(self.modelLogLikelihood())
         hooked = any(getattr(type(self), n) is not getattr(GpuLDASampler, n)
                      for n in ("preIteration", "postIteration", "preZ", "postZ", "prePhi", "postPhi"))
+        per_call = self.SWEEPS_PER_CALL if chunk is None else chunk
         step = max(1, cfg.topic_interval) if cfg.compute_likelihood else iterations
+        if per_call > 0:
+            step = min(step, per_call)
+        t_start = sum(self.getTimers())
         done_total = 0
         while done_total < iterations and not self.getAbort():
             n = min(step, iterations - done_total)
+            if cfg.compute_likelihood:   # keep the log-likelihood on its topic_interval grid
+                n = min(n, max(1, cfg.topic_interval) - done_total % max(1, cfg.topic_interval))
             if cfg.start_diagnostic > 0:
                 # the diagnostic block runs after every sweep from start_diagnostic on (UPL:707-823)
                 it = self.getCurrentIteration()
@@ -266,7 +280,8 @@ class GpuLDASampler:
             else:
                 d = C.c_int32(0)
                 if z_out is not None and done_total + n >= iterations:
-                    self._ck(self._L.ldagpu_sweep_get_z(self._h, n, C.byref(d), ptr(z_out)))
+                    fn = self._L.ldagpu_sweep_get_z16 if z16 else self._L.ldagpu_sweep_get_z
+                    self._ck(fn(self._h, n, C.byref(d), ptr(z_out)))
                     z_filled = True
                 else:
                     self._ck(self._L.ldagpu_sweep(self._h, n, C.byref(d)))
@@ -279,11 +294,10 @@ class GpuLDASampler:
                 self._log_likelihood_to_file(self.loglikelihood[-1])                          # UPL:846-850
             if done < n:
                 break
-            z_ms, c_ms, p_ms, _ = self.getTimers()
-            if (z_ms + c_ms + p_ms) / 1000.0 >= cfg.exec_time > 0:        # UPL:926-928
+            if (sum(self.getTimers()) - t_start) / 1000.0 >= cfg.exec_time > 0:        # UPL:926-928
                 break
         if z_out is not None and not z_filled:
-            self._ck(self._L.ldagpu_get_z(self._h, ptr(z_out)))
+            self._ck((self._L.ldagpu_get_z16 if z16 else self._L.ldagpu_get_z)(self._h, ptr(z_out)))
         self.postSample()
 
     def _one_hooked_sweep(self):
@@ -334,6 +348,14 @@ class GpuLDASampler:
             # UPL:1828-1830
             raise ValueError(f"Count does not sum to nr. types! Sumtotal: {len(z)} no.types: {len(self._tokens)}")
         self._ck(self._L.ldagpu_set_z(self._h, ptr(z), 1 if redraw_phi else 0))
+
+    def set_z16_flat(self, z: np.ndarray, redraw_phi: bool = True):
+        """setZIndicators with the indicators held as uint16 on the host (K <= 65 536): half the PCIe bytes."""
+        self._need()
+        z = np.ascontiguousarray(z, np.uint16)
+        if len(z) != len(self._tokens):
+            raise ValueError(f"Count does not sum to nr. types! Sumtotal: {len(z)} no.types: {len(self._tokens)}")
+        self._ck(self._L.ldagpu_set_z16(self._h, ptr(z), 1 if redraw_phi else 0))
 
     def getZIndicators(self) -> List[np.ndarray]:
         """MSL:464-477: int[D][] (local documents)."""

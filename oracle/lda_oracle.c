@@ -290,8 +290,8 @@ void oracle_doc_topic_counts(int64_t D, const int64_t *doc_off, const int32_t *z
  *   inside the chosen tile: Kogge-Stone inclusive scan of its 32 lane totals.
  * Search tile -> lane -> element; clamp to K-1.
  * ------------------------------------------------------------------------------------------ */
-static int32_t draw_topic_contract(const float *a, const float *phirow, int32_t K, float U,
-                                   float *scratch /* NT*128 + ceil(NT/8)*33 floats */)
+static int32_t draw_topic_contract_tiles(const float *a, const float *phirow, int32_t K, float U,
+                                         float *scratch /* NT*128 + ceil(NT/8)*33 floats */)
 {
     int NT = (K + 127) / 128;
     int NG = (NT + 7) / 8;
@@ -374,6 +374,57 @@ static int32_t draw_topic_contract(const float *a, const float *phirow, int32_t 
     return k < K ? k : K - 1;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Categorical draw of the contract for K <= 1024 ("lane-contiguous" tree; the
+ * register path of the z kernel).  NT = 1, 2, 4 or 8 tiles (the smallest with 128*NT >= K),
+ * L = 4*NT; lane l of 32 owns the L CONSECUTIVE topics [l*L, (l+1)*L):
+ *   lane-local sequential prefix p_0 = a*phi, p_m = fma(a_m, phi_m, p_{m-1}) (padding topics k >= K
+ *     leave the prefix unchanged);
+ *   Kogge-Stone inclusive scan of the 32 lane totals (offsets 1, 2, 4, 8, 16): S = scan[31];
+ *   u = U*S; lane = first l with scan[l] >= u; r = u - scan[l-1]; element = first m with p_m >= r.
+ * Same selection rule as the reference's walk (first k with cumsum_k >= U*sum), natural topic order.
+ * ------------------------------------------------------------------------------------------ */
+static int lanes_tiles(int32_t K) { return K <= 128 ? 1 : K <= 256 ? 2 : K <= 512 ? 4 : 8; }
+
+static int32_t draw_topic_contract_lanes(const float *a, const float *phirow, int32_t K, float U)
+{
+    const int L = 4 * lanes_tiles(K);
+    float p[32][32], x[32], y[32];
+    for (int l = 0; l < 32; ++l) {
+        float run = 0.0f;
+        for (int m = 0; m < L; ++m) {
+            int k = l * L + m;
+            if (m == 0) run = (k < K) ? a[k] * phirow[k] : 0.0f;
+            else if (k < K) run = fmaf(a[k], phirow[k], run);
+            p[l][m] = run;
+        }
+        x[l] = run;
+    }
+    for (int off = 1; off < 32; off <<= 1) {
+        for (int l = 0; l < 32; ++l) y[l] = (l >= off) ? x[l] + x[l - off] : x[l];
+        memcpy(x, y, sizeof x);
+    }
+    float S = x[31];
+    float u = U * S;
+    int ls = 31;
+    for (int l = 0; l < 32; ++l)
+        if (x[l] >= u) { ls = l; break; }
+    float r = u - (ls > 0 ? x[ls - 1] : 0.0f);
+    int ms = L - 1;
+    for (int m = 0; m < L; ++m)
+        if (p[ls][m] >= r) { ms = m; break; }
+    int32_t k = ls * L + ms;
+    return k < K ? k : K - 1;
+}
+
+/* two regimes, like the kernels: K <= 1024 keeps the row in registers (lane-contiguous tree),
+ * larger K walks it in shared memory tile by tile (tile tree) */
+static int32_t draw_topic_contract(const float *a, const float *phirow, int32_t K, float U, float *scratch)
+{
+    return K <= 1024 ? draw_topic_contract_lanes(a, phirow, K, U)
+                     : draw_topic_contract_tiles(a, phirow, K, U, scratch);
+}
+
 int32_t oracle_draw_topic_contract(const float *a, const float *phirow, int32_t K, float U)
 {
     int NT = (K + 127) / 128;
@@ -428,11 +479,19 @@ void oracle_theta_contract(int64_t D, const int64_t *doc_off, const int32_t *z, 
             float acc[32], t[32];
             for (int l = 0; l < 32; ++l) {
                 float s = 0.0f;
-                for (int j = 0; j < NT; ++j)
-                    for (int i = 0; i < 4; ++i) {
-                        int k = 128 * j + 4 * l + i;
+                if (K <= 1024) {   /* lane l owns the consecutive topics [l*L, (l+1)*L) */
+                    const int L = 4 * lanes_tiles(K);
+                    for (int m = 0; m < L; ++m) {
+                        int k = l * L + m;
                         if (k < K) s = s + th[k];
                     }
+                } else {
+                    for (int j = 0; j < NT; ++j)
+                        for (int i = 0; i < 4; ++i) {
+                            int k = 128 * j + 4 * l + i;
+                            if (k < K) s = s + th[k];
+                        }
+                }
                 acc[l] = s;
             }
             for (int off = 16; off >= 1; off >>= 1) {
