@@ -61,6 +61,21 @@ int ldagpu_create(int32_t K, int32_t V, int64_t D, const int64_t *doc_offsets, c
                   int64_t doc_base, int64_t token_base, ldagpu_handle *out);
 int ldagpu_destroy(ldagpu_handle h);
 
+/*
+ * The same from ONE caller thread for several GPUs of one box: the reference runs one coordinator thread in one JVM
+ * (tui/ParallelLDA.java:173-202 -> UPL:552-943), so `scheme = gpu_ggs` with `gpu_devices = 0,1,...` must not need one
+ * process per GPU.  Takes the WHOLE corpus; documents are sharded by token count into contiguous ranges, one per
+ * device (devices == NULL: ordinals 0..n_devices-1; n_devices in {1, 2, 4, 8}); every other entry point takes the
+ * returned handle and works on the whole corpus (z, theta and the document-topic matrix in corpus order).  The
+ * count exchange and the Phi broadcast run inside the Phi kernels over direct peer pointers (no NCCL, no IPC), so
+ * the devices need peer access (NVLink / NVSwitch); results are bit-identical to one GPU and to one process per GPU.
+ */
+int ldagpu_create_multi(int32_t K, int32_t V, int64_t D, const int64_t *doc_offsets, const int32_t *tokens,
+                        const double *alpha, double beta, uint64_t seed, int32_t scheme, int32_t n_devices,
+                        const int32_t *devices, ldagpu_handle *out);
+/* how the corpus is sharded behind the handle: *n_shards, and (first_docs != NULL) the n_shards + 1 document bounds */
+int ldagpu_get_shards(ldagpu_handle h, int32_t *n_shards, int64_t *first_docs);
+
 /* multi-GPU (one process per GPU).  Rank 0 makes an id, the host program broadcasts its 128 bytes
  * (torch.distributed / any rendezvous), every rank joins.  After this, sweeps exchange counts with
  * one reduce-scatter and Phi with one all-gather per sweep. */
@@ -127,6 +142,18 @@ int ldagpu_set_phi(ldagpu_handle h, const double *phi);
  * iteration > burn_in && iteration % thin == 0 (UPL:1350-1352); burn_in <= 0 disables. */
 int ldagpu_set_phi_mean_schedule(ldagpu_handle h, int32_t burn_in, int32_t thin);
 int ldagpu_get_phi_mean(ldagpu_handle h, double *phi_mean, int32_t *n_sampled);
+/* How the rows of Phi are drawn (before ldagpu_init_z_java_random / ldagpu_set_z, which draw the first Phi):
+ *   LDAGPU_PHI_GAMMA      Dirichlet = Gammas + normalise + floor (GGS:182-192, PCGS:91-101, types/ParallelDirichlet.java:46-70)
+ *   LDAGPU_PHI_POLYA_URN  the Poisson Polya urn of scheme "polyaurn" (topics/PolyaUrnSpaliasLDA.java:495-507,
+ *                         types/PolyaUrnDirichletFixedCoeffPoisson.java:17-44): X = Poisson(beta + n_wk), phi = X / sum X,
+ *                         zeros stay zeros; alias_poisson_threshold = the reference's key of that name (default 100,
+ *                         types/PoissonFixedCoeffSampler.java:45-51): counts below it are drawn exactly, from it on by
+ *                         the normal approximation.  Use with LDAGPU_SCHEME_SPALIAS (the reference pairs it with the
+ *                         sparse z-step); a word type whose Phi column is all zero falls back to a uniform topic
+ *                         (PolyaUrnSpaliasLDA.java:275-277). */
+#define LDAGPU_PHI_GAMMA 0
+#define LDAGPU_PHI_POLYA_URN 1
+int ldagpu_set_phi_sampler(ldagpu_handle h, int32_t sampler, int32_t alias_poisson_threshold);
 /* GGS thetaMatrix (UPL:78, GGS:72): double[D][K] of the last sweep; set = test injection */
 int ldagpu_get_theta(ldagpu_handle h, double *theta);
 int ldagpu_set_theta(ldagpu_handle h, const double *theta);
@@ -134,6 +161,16 @@ int ldagpu_set_theta(ldagpu_handle h, const double *theta);
 int ldagpu_log_likelihood(ldagpu_handle h, double *ll);
 /* computeLogPosterior (UPL:1573-1634); GGS uses the sweep's theta (UPL:716-720) */
 int ldagpu_log_posterior(ldagpu_handle h, double *lp);
+
+/* Hooks for the hyper-parameter optimisation (MSL:812-905, called every hyperparam_optim_interval sweeps, UPL:891-894;
+ * off by default).  MALLET's fixed-point iteration (Dirichlet.learnParameters / learnSymmetricConcentration) stays on the
+ * host; the library supplies the histograms it consumes -- doc_topic_hist[c] = number of (document, topic) pairs with
+ * n_dk = c (MSL:815-846 documentTopicHistogram merged over topics), type_topic_hist[c] = number of (type, topic) cells
+ * with n_wk = c (MSL:860-875 countHistogram); counts beyond the last bin land in it -- and takes the new values back. */
+int ldagpu_get_count_histograms(ldagpu_handle h, int32_t n_doc_bins, int64_t *doc_topic_hist, int32_t n_type_bins,
+                                int64_t *type_topic_hist);
+int ldagpu_set_alpha(ldagpu_handle h, const double *alpha /* [K] */);
+int ldagpu_set_beta(ldagpu_handle h, double beta);
 
 /* abort()/getAbort() (topics/AbortableSampler.java:3-6, MSL:601-608); async-safe */
 int ldagpu_abort(ldagpu_handle h);

@@ -21,7 +21,7 @@ SYMBOLS = [
     "ldagpu_set_phi_mean_schedule", "ldagpu_get_phi_mean", "ldagpu_get_theta", "ldagpu_set_theta",
     "ldagpu_log_likelihood", "ldagpu_log_posterior", "ldagpu_abort", "ldagpu_get_abort",
     "ldagpu_get_timers", "ldagpu_get_last_call_stats",
-    "ldagpu_set_z16", "ldagpu_get_z16", "ldagpu_sweep_get_z16",
+    "ldagpu_set_z16", "ldagpu_get_z16", "ldagpu_sweep_get_z16", "ldagpu_create_multi", "ldagpu_get_shards", "ldagpu_set_phi_sampler", "ldagpu_get_count_histograms", "ldagpu_set_alpha", "ldagpu_set_beta",
 ]
 
 
@@ -54,6 +54,8 @@ def load() -> C.CDLL:
     sig("ldagpu_last_error", C.c_char_p, vp)
     sig("ldagpu_device_count", C.c_int)
     sig("ldagpu_create", C.c_int, i32, i32, i64, vp, vp, vp, f64, u64, i32, i32, i64, i64, C.POINTER(vp))
+    sig("ldagpu_create_multi", C.c_int, i32, i32, i64, vp, vp, vp, f64, u64, i32, i32, vp, C.POINTER(vp))
+    sig("ldagpu_get_shards", C.c_int, vp, pi32, vp)
     sig("ldagpu_destroy", C.c_int, vp)
     sig("ldagpu_comm_unique_id", C.c_int, vp)
     sig("ldagpu_comm_init", C.c_int, vp, i32, i32, vp)
@@ -76,6 +78,10 @@ def load() -> C.CDLL:
               "ldagpu_get_phi", "ldagpu_set_phi", "ldagpu_get_theta", "ldagpu_set_theta"):
         sig(n, C.c_int, vp, vp)
     sig("ldagpu_set_phi_mean_schedule", C.c_int, vp, i32, i32)
+    sig("ldagpu_set_phi_sampler", C.c_int, vp, i32, i32)
+    sig("ldagpu_get_count_histograms", C.c_int, vp, i32, vp, i32, vp)
+    sig("ldagpu_set_alpha", C.c_int, vp, vp)
+    sig("ldagpu_set_beta", C.c_int, vp, f64)
     sig("ldagpu_get_phi_mean", C.c_int, vp, vp, pi32)
     sig("ldagpu_log_likelihood", C.c_int, vp, pf64)
     sig("ldagpu_log_posterior", C.c_int, vp, pf64)

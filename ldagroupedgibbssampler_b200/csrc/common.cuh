@@ -114,11 +114,12 @@ cudaError_t launch_p2p_wait(const PeerTable &pt, int kind, uint32_t epoch, cudaS
 // fused variants of the three Phi kernels (kernels_phi.cu)
 cudaError_t launch_phi_draw_p2p(const PeerTable &pt, bool reduce_counts, uint32_t epoch_counts, const Dims &dm,
                                 int32_t *n_wk, int32_t *n_k, double beta, float *phiT, double *partial, int32_t row0,
-                                int32_t row1, uint32_t seed_lo, uint32_t seed_hi, uint32_t sweep, cudaStream_t st);
+                                int32_t row1, uint32_t seed_lo, uint32_t seed_hi, uint32_t sweep, int32_t poisson_L,
+                                cudaStream_t st);
 cudaError_t launch_phi_segment_sums_p2p(const PeerTable &pt, uint32_t epoch_seg, const Dims &dm, const double *partial,
                                         int seg0, int seg1, cudaStream_t st);
 cudaError_t launch_phi_normalise_p2p(const PeerTable &pt, uint32_t epoch_seg, uint32_t epoch_phi, const Dims &dm,
-                                     double *topic_sum, double *phi_mean_sum, int32_t row0, int32_t row1,
+                                     double *topic_sum, double *phi_mean_sum, int32_t row0, int32_t row1, int keep_zeros,
                                      cudaStream_t st);
 
 // Opt a kernel into `smem` bytes of dynamic shared memory and report how many CTAs of `threads` threads fit
@@ -184,13 +185,13 @@ cudaError_t launch_doc_topic_counts(const Dims &dm, const int64_t *doc_off, cons
 // Phi draw over rows [row0, row1) (multiples of 64); partial[(row/8)][Ks] fp64
 cudaError_t launch_phi_draw(const Dims &dm, const int32_t *n_wk, double beta, float *phiT,
                             double *partial, int32_t row0, int32_t row1, uint32_t seed_lo,
-                            uint32_t seed_hi, uint32_t sweep, cudaStream_t st);
+                            uint32_t seed_hi, uint32_t sweep, int32_t poisson_L /* > 0: Polya-urn Poisson draw */, cudaStream_t st);
 // segment sums seg[s][Ks] for segments [seg0, seg1)
 cudaError_t launch_phi_segment_sums(const Dims &dm, const double *partial, double *seg, int seg0,
                                     int seg1, cudaStream_t st);
 // S_k from the 8 segment sums, then normalise rows [row0,row1) and optionally add into phi_sum
 cudaError_t launch_phi_normalise(const Dims &dm, const double *seg, double *topic_sum, float *phiT,
-                                 double *phi_mean_sum, int32_t row0, int32_t row1, cudaStream_t st);
+                                 double *phi_mean_sum, int32_t row0, int32_t row1, int keep_zeros, cudaStream_t st);
 // log-likelihood pieces: per-block partial sums (ll_type: pairs {sum, nnz})
 cudaError_t launch_lgs_table(int K, const double *alpha, double *out /*[K] lgS(alpha_k)*/, cudaStream_t st);
 cudaError_t launch_ll_doc(const Dims &dm, const int64_t *doc_off, const int32_t *z,
@@ -198,6 +199,10 @@ cudaError_t launch_ll_doc(const Dims &dm, const int64_t *doc_off, const int32_t 
                           int n_partials, int sm_count, cudaStream_t st);
 cudaError_t launch_ll_type(const Dims &dm, const int32_t *n_wk, double beta, int32_t row0,
                            int32_t row1, double *partials, int n_partials, cudaStream_t st);
+// histograms of the count values for the hyper-parameter optimisation (ModifiedSimpleLDA.java:812-905)
+cudaError_t launch_count_histograms(const Dims &dm, const int64_t *doc_off, const int32_t *z, const int32_t *n_wk,
+                                    int32_t row0, int32_t row1, unsigned long long *doc_hist, int n_doc_bins,
+                                    unsigned long long *type_hist, int n_type_bins, cudaStream_t st);
 // log-posterior pieces (UncollapsedParallelLDA.java:1573-1634)
 cudaError_t launch_lp_tokens(const Dims &dm, const int32_t *tokens, const int32_t *z,
                              const float *phiT, double *partials, int n_partials, cudaStream_t st);

@@ -15,7 +15,7 @@
 
 namespace ldagpu {
 
-enum : uint32_t { STREAM_Z = 1, STREAM_THETA = 2, STREAM_PHI = 3 };
+enum : uint32_t { STREAM_Z = 1, STREAM_THETA = 2, STREAM_PHI = 3, STREAM_POISSON = 4 };
 
 // ---------------------------------------------------------------------------------------
 // Philox4x32-10 counter-based generator
@@ -320,6 +320,124 @@ __device__ __forceinline__ bool gamma_attempt_squeeze(bool boost, T d, T c, T in
     return true;
 }
 
+// ---------------------------------------------------------------------------------------
+// The squeeze-only attempt for W cells at once (fp32).  Operation for operation the same arithmetic as
+// gamma_attempt_squeeze<float> -- every cell sees exactly the scalar sequence, so the values are bit-identical --
+// but written with the W cells side by side: the polynomial and Philox chains of one cell are strictly
+// dependent, and a warp that works on one cell at a time spends most of its cycles waiting on fixed-latency
+// results (ncu: stall_wait 28 % of the fused z kernel).  W independent chains in one basic block let the
+// scheduler overlap them.  Inputs of the logarithms are uniforms (n + 1/2) 2^-23 >= 2^-24: never denormal, so
+// the denormal branch of c_ln is not needed here.
+// ---------------------------------------------------------------------------------------
+template <int W> __device__ __forceinline__ void c_ln_normal_w(const float (&x)[W], float (&out)[W])
+{
+    using M = CM<float>;
+    float m[W], s[W], s2[W], p[W], ef[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        const uint32_t t = M::bits(x[w]) - M::SQRT_HALF;
+        ef[w] = M::from_int((int32_t)t >> M::MANT);
+        m[w] = M::from((t & M::MANT_MASK) + M::SQRT_HALF);
+    }
+#pragma unroll
+    for (int w = 0; w < W; ++w) s[w] = M::div(M::sub(m[w], 1.0f), M::add(m[w], 1.0f));
+#pragma unroll
+    for (int w = 0; w < W; ++w) { s2[w] = M::mul(s[w], s[w]); p[w] = coef_odd<float>(M::LN_TERMS - 1); }
+#pragma unroll
+    for (int n = M::LN_TERMS - 2; n >= 0; --n)
+#pragma unroll
+        for (int w = 0; w < W; ++w) p[w] = M::fma(p[w], s2[w], coef_odd<float>(n));
+#pragma unroll
+    for (int w = 0; w < W; ++w)
+        out[w] = M::fma(ef[w], 0.693147180559945309417232121458f, M::mul(M::mul(2.0f, s[w]), p[w]));
+}
+
+template <int W> __device__ __forceinline__ void c_exp_neg_w(const float (&y)[W], float (&out)[W])
+{
+    using M = CM<float>;
+    float n[W], r[W], p[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        n[w] = M::rint(M::mul(y[w], 1.44269504088896340735992468100f));
+        r[w] = M::fma(-n[w], M::ln2_hi(), y[w]);
+        r[w] = M::fma(-n[w], M::ln2_lo(), r[w]);
+        p[w] = coef_invfact<float>(M::EXP_DEG);
+    }
+#pragma unroll
+    for (int k = M::EXP_DEG - 1; k >= 0; --k)
+#pragma unroll
+        for (int w = 0; w < W; ++w) p[w] = M::fma(p[w], r[w], coef_invfact<float>(k));
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        // below the cutoff the scalar version returns 0 before it forms the scale factors; clamp n so that the
+        // exponent arithmetic stays in range on the discarded path
+        const bool tiny = y[w] < M::exp_cutoff();
+        const int32_t ni = tiny ? 0 : M::to_int(n[w]);
+        const int32_t n1 = ni >> 1, n2 = ni - n1;
+        const float s1 = M::from((uint32_t)(n1 + M::BIAS) << M::MANT);
+        const float s2 = M::from((uint32_t)(n2 + M::BIAS) << M::MANT);
+        const float v = M::mul(M::mul(p[w], s1), s2);
+        out[w] = tiny ? 0.0f : v;
+    }
+}
+
+template <int W> __device__ __forceinline__ void c_cos2pi_w(const uint32_t (&wd)[W], float (&out)[W])
+{
+    using M = CM<float>;
+    float a[W], a2[W], p[W];
+    bool use_sin[W], neg[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        const uint32_t o = wd[w] >> 29;
+        const bool odd = (o & 1u) != 0;
+        use_sin[w] = (((o + 1u) >> 1) & 1u) != 0;
+        neg[w] = (o >= 2u && o <= 5u);
+        a[w] = M::mul(M::ang_frac(wd[w], odd), 0.785398163397448309615660845820f);
+        a2[w] = M::mul(a[w], a[w]);
+        p[w] = use_sin[w] ? coef_sin<float>(M::TRIG_DEG) : coef_cos<float>(M::TRIG_DEG);
+    }
+#pragma unroll
+    for (int k = M::TRIG_DEG - 1; k >= 0; --k)
+#pragma unroll
+        for (int w = 0; w < W; ++w) p[w] = M::fma(p[w], a2[w], use_sin[w] ? coef_sin<float>(k) : coef_cos<float>(k));
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        if (use_sin[w]) p[w] = M::mul(p[w], a[w]);
+        out[w] = neg[w] ? -p[w] : p[w];
+    }
+}
+
+// done[w] = the squeeze accepted cell w's attempt-0 candidate, g[w] its Gamma value (boost applied when inva > 0)
+template <int W>
+__device__ __forceinline__ void gamma_attempt_squeeze_w(const float (&d)[W], const float (&c)[W], const float (&inva)[W],
+                                                        const uint4 (&rnd)[W], bool (&done)[W], float (&g)[W])
+{
+    using M = CM<float>;
+    float u1[W], l1[W], cs[W], x[W], v[W], ub[W], lb[W], eb[W];
+    uint32_t ang[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) { u1[w] = M::uni(rnd[w].x); ang[w] = rnd[w].y; ub[w] = M::uni(rnd[w].w); }
+    c_ln_normal_w<W>(u1, l1);
+    c_cos2pi_w<W>(ang, cs);
+    c_ln_normal_w<W>(ub, lb);
+#pragma unroll
+    for (int w = 0; w < W; ++w) x[w] = M::mul(M::sqrt(M::mul(-2.0f, l1[w])), cs[w]);
+#pragma unroll
+    for (int w = 0; w < W; ++w) lb[w] = M::mul(lb[w], inva[w]);
+    c_exp_neg_w<W>(lb, eb);
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        v[w] = M::fma(c[w], x[w], 1.0f);
+        const float x2 = M::mul(x[w], x[w]);
+        const float x4 = M::mul(x2, x2);
+        const float u = M::uni(rnd[w].z);
+        done[w] = (v[w] > 0.0f) && (u < M::fma(-0.0331f, x4, 1.0f));
+        const float v3 = M::mul(M::mul(v[w], v[w]), v[w]);
+        const float gv = M::mul(d[w], v3);
+        g[w] = inva[w] > 0.0f ? M::mul(gv, eb[w]) : gv;
+    }
+}
+
 template <typename T> __device__ __forceinline__ void gamma_setup(T a, bool &boost, T &d, T &c, T &inva)
 {
     using M = CM<T>;
@@ -342,6 +460,48 @@ __device__ __forceinline__ T c_gamma(T a, uint32_t k0, uint32_t k1, unsigned lon
         uint4 w = philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), sweep, (stream << 24) | attempt, k0, k1);
         if (gamma_attempt<T>(boost, d, c, inva, w, g)) return g;
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// Poisson draw of the Polya-urn Phi sampler (reference: types/PolyaUrnDirichletFixedCoeffPoisson.java:17-44 draws
+// X_w ~ Poisson(beta + n_wk) per cell through types/PoissonFixedCoeffSampler.java:45-51: an alias table over the
+// Poisson pmf truncated to [0, 2L) when n < L, and round(sqrt(lambda) N(0,1) + lambda) -- the normal approximation
+// of PolyaUrnDirichlet.java:102-107 -- from L on; L = alias_poisson_threshold).  Contract: one Philox block per
+// cell, fp64, libm-free:
+//   n <  L   inversion by sequential search over the same truncated pmf with ONE 52-bit uniform:
+//            p = exp(-lambda), F = p, k = 0; while (u > F && k < 2L-1) { k++; p *= lambda / k; F += p; }
+//            (exactly the distribution the alias table encodes; a zero-count cell, lambda = beta << 1, stops at
+//            k = 0 with probability exp(-beta) after one comparison)
+//   n >= L   floor(sqrt(lambda) * x + lambda + 1/2) with x = sqrt(-2 ln u1) cos(2 pi t) (Java's Math.round), at least 0
+// p0 = exp(-beta) is passed in so that the zero-count cells do not re-evaluate it.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double uniform52(uint32_t hi, uint32_t lo)
+{
+    const unsigned long long n = ((unsigned long long)hi << 20) | (unsigned long long)(lo >> 12);
+    return __dmul_rn(__dadd_rn(__ull2double_rn(n), 0.5), 0x1p-52);
+}
+
+__device__ __forceinline__ int32_t c_poisson(double beta, int32_t n, int32_t L, double p0, uint4 w)
+{
+    const double lambda = __dadd_rn(beta, __int2double_rn(n));
+    if (n < L) {
+        const double u = uniform52(w.x, w.y);
+        double p = n == 0 ? p0 : c_exp_neg<double>(-lambda);
+        double F = p;
+        int32_t k = 0;
+        const int32_t kmax = 2 * L - 1;
+        while (u > F && k < kmax) {
+            ++k;
+            p = __dmul_rn(p, __ddiv_rn(lambda, __int2double_rn(k)));
+            F = __dadd_rn(F, p);
+        }
+        return k;
+    }
+    const double u1 = CM<double>::uni(w.x);
+    const double x = __dmul_rn(__dsqrt_rn(__dmul_rn(-2.0, c_ln<double>(u1))), c_cos2pi<double>(w.y));
+    const double v = __dadd_rn(__fma_rn(__dsqrt_rn(lambda), x, lambda), 0.5);
+    const double r = floor(v);
+    return r > 0.0 ? (int32_t)__double2int_rz(r) : 0;
 }
 
 }  // namespace ldagpu

@@ -147,6 +147,7 @@ struct ldagpu_handle_s {
     std::vector<int64_t> h_doc_off;
 
     int32_t mean_burn_in = 0, mean_thin = 1, n_sampled_phi = 0;
+    int32_t poisson_L = 0;   // > 0: Phi rows are drawn by the Poisson Polya urn (ldagpu_set_phi_sampler)
 
     cudaStream_t stream = nullptr;
     std::vector<cudaEvent_t> events;
@@ -165,7 +166,13 @@ struct ldagpu_handle_s {
     std::vector<void *> ipc_opened;
     uint32_t ep[P2P_FLAG_KINDS] = {0, 0, 0, 0};
     uint32_t counts_epoch = 0;   // epoch of the last "counts complete" signal (consumed by the reduce)
+    uint32_t bar_epoch = 0, seg_epoch = 0, phi_epoch = 0;   // epochs in flight between the stages of an exchange
     std::string p2p_note;
+
+    // single-process multi-GPU (ldagpu_create_multi): this handle only coordinates; the shards hold the state
+    std::vector<ldagpu_handle> shards;
+    std::vector<int64_t> shard_doc0, shard_tok0;   // [G+1] first document / token of every shard
+    bool multi() const { return !shards.empty(); }
 
     std::atomic<int> abort_flag{0};
     std::string err;
@@ -288,31 +295,58 @@ int step_counts_local(ldagpu_handle h)
 // between the ranks -- one rank still generating its shard, replaying java.util.Random for a later shard --
 // must not reach them.  Every API call that exchanges starts with one tiny NCCL all-reduce, which waits as
 // long as it takes; after it the ranks are microseconds apart and the flag waits only absorb compute skew.
-int rendezvous(ldagpu_handle h)
+int rendezvous(ldagpu_handle h, int *abort_any = nullptr)
 {
-    if (!h->p2p) return 0;
-    NK(h, g_nccl.AllReduce(h->p2p_local.p + P2P_FLAG_KINDS + 1, h->p2p_local.p + P2P_FLAG_KINDS + 1, 1, ncclInt32, ncclSum,
-                           h->comm, h->stream));
+    if (abort_any) *abort_any = h->abort_flag.load(std::memory_order_relaxed);
+    if (h->world == 1 || !h->comm) return 0;   // single GPU, or shards driven by one caller thread (no skew to absorb)
+    if (!h->p2p && !abort_any) return 0;       // the NCCL collectives wait as long as it takes anyway
+    uint32_t *word = h->p2p_local.p + P2P_FLAG_KINDS + 1;
+    uint32_t mine = abort_any ? (uint32_t)(*abort_any != 0) : 0u;
+    CK(h, cudaMemcpyAsync(word, &mine, sizeof mine, cudaMemcpyHostToDevice, h->stream));
+    NK(h, g_nccl.AllReduce(word, word, 1, ncclUint32, ncclMax, h->comm, h->stream));
+    if (abort_any) {
+        CK(h, cudaMemcpyAsync(&mine, word, sizeof mine, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        *abort_any = (int)mine;
+    }
     return 0;
 }
 
+// Stages.  With several shards driven by ONE caller thread (ldagpu_create_multi) a kernel that waits, on the device,
+// for another shard's signal must only be enqueued after the kernel that gives the signal: a launch can block the
+// host until the device drains (first use of a kernel under lazy module loading, a larger local-memory pool), and a
+// device that waits for work the blocked host has not enqueued yet would never drain.  So the exchange and the Phi
+// draw are cut into stages -- every waiter in a later stage than the signals it waits for -- and the multi-GPU layer
+// runs stage by stage over all shards.  stage < 0 runs all stages (one shard per caller: nothing to order).
+enum { EXCH_STAGES = 3, PHI_STAGES = 3 };
+
 // defer_reduce (peer-memory mode): only announce the partial counts; the Phi draw that follows sums them.
-int step_counts_exchange(ldagpu_handle h, bool defer_reduce)
+//   stage 0  push n_k parts + "my partial counts are complete"
+//   stage 1  reduce the rank's vocabulary rows over all ranks' counts (waits for stage 0 of all), signal the barrier
+//   stage 2  wait for the barrier: nobody touches its partial counts again before every rank has read them
+int step_counts_exchange(ldagpu_handle h, bool defer_reduce, int stage = -1)
 {
     if (h->world == 1) return 0;
     if (h->p2p) {
-        h->counts_epoch = ++h->ep[P2P_FLAG_COUNTS];
-        CK(h, launch_p2p_push_topic_totals(h->pt, h->n_k.p, h->dm.Ks, h->counts_epoch, h->stream));
-        h->last_launches += 1;
+        if (stage < 0 || stage == 0) {
+            h->counts_epoch = ++h->ep[P2P_FLAG_COUNTS];
+            CK(h, launch_p2p_push_topic_totals(h->pt, h->n_k.p, h->dm.Ks, h->counts_epoch, h->stream));
+            h->last_launches += 1;
+        }
         if (defer_reduce) return 0;
-        CK(h, launch_p2p_reduce_counts(h->pt, h->dm, h->n_k.p, h->row0, h->row1, h->counts_epoch, h->sm_count, h->stream));
-        // nobody may touch its partial counts again before every rank has read them
-        const uint32_t e = ++h->ep[P2P_FLAG_BAR];
-        CK(h, launch_p2p_signal(h->pt, P2P_FLAG_BAR, e, h->stream));
-        CK(h, launch_p2p_wait(h->pt, P2P_FLAG_BAR, e, h->stream));
-        h->last_launches += 3;
+        if (stage < 0 || stage == 1) {
+            CK(h, launch_p2p_reduce_counts(h->pt, h->dm, h->n_k.p, h->row0, h->row1, h->counts_epoch, h->sm_count, h->stream));
+            h->bar_epoch = ++h->ep[P2P_FLAG_BAR];
+            CK(h, launch_p2p_signal(h->pt, P2P_FLAG_BAR, h->bar_epoch, h->stream));
+            h->last_launches += 2;
+        }
+        if (stage < 0 || stage == 2) {
+            CK(h, launch_p2p_wait(h->pt, P2P_FLAG_BAR, h->bar_epoch, h->stream));
+            h->last_launches += 1;
+        }
         return 0;
     }
+    if (stage > 0) return 0;
     const size_t slice = (size_t)(h->dm.Vp / h->world) * h->dm.Ks;
     NK(h, g_nccl.ReduceScatter(h->n_wk.p, h->n_wk.p + (size_t)h->rank * slice, slice, ncclInt32, ncclSum, h->comm, h->stream));
     NK(h, g_nccl.AllReduce(h->n_k.p, h->n_k.p, (size_t)h->dm.Ks, ncclInt32, ncclSum, h->comm, h->stream));
@@ -331,35 +365,48 @@ int phi_mean_buffer(ldagpu_handle h, bool accumulate_mean, double **mean)
     return 0;
 }
 
-// peer-memory mode: draw (summing the peers' partial counts when fused_reduce), segment sums stored to
-// every rank, normalise + store the rows to every rank, wait until every rank's rows have landed here
-int step_phi_p2p(ldagpu_handle h, bool accumulate_mean, cudaEvent_t *ev, bool fused_reduce)
+// peer-memory mode:
+//   stage 0  draw (summing the peers' partial counts when fused_reduce: waits for their "counts complete"), segment
+//            sums stored to every rank + "segments of rank r are in place"
+//   stage 1  normalise (waits for every rank's segments) + store the rows to every rank + "rows of rank r are in place"
+//   stage 2  wait until every rank's rows have landed here; [sparse scheme] rebuild the alias tables
+int step_phi_p2p(ldagpu_handle h, bool accumulate_mean, cudaEvent_t *ev, bool fused_reduce, int stage)
 {
     const uint32_t lo = (uint32_t)h->seed, hi = (uint32_t)(h->seed >> 32);
-    CK(h, launch_phi_draw_p2p(h->pt, fused_reduce, h->counts_epoch, h->dm, h->n_wk.p, h->n_k.p, h->beta, h->phiT.p,
-                              h->partial.p, h->row0, h->row1, lo, hi, (uint32_t)h->iteration, h->stream));
-    const uint32_t e_seg = ++h->ep[P2P_FLAG_SEG];
-    CK(h, launch_phi_segment_sums_p2p(h->pt, e_seg, h->dm, h->partial.p, h->seg0, h->seg1, h->stream));
-    if (ev) { CK(h, cudaEventRecord(ev[0], h->stream)); CK(h, cudaEventRecord(ev[1], h->stream)); }
-    double *mean = nullptr;
-    if (phi_mean_buffer(h, accumulate_mean, &mean)) return 1;
-    const uint32_t e_phi = ++h->ep[P2P_FLAG_PHI];
-    CK(h, launch_phi_normalise_p2p(h->pt, e_seg, e_phi, h->dm, h->topic_sum.p, mean, h->row0, h->row1, h->stream));
-    if (ev) CK(h, cudaEventRecord(ev[2], h->stream));
-    CK(h, launch_p2p_wait(h->pt, P2P_FLAG_PHI, e_phi, h->stream));
-    h->last_launches += 4;
-    if (step_alias(h)) return 1;
-    if (ev) CK(h, cudaEventRecord(ev[3], h->stream));
+    if (stage < 0 || stage == 0) {
+        CK(h, launch_phi_draw_p2p(h->pt, fused_reduce, h->counts_epoch, h->dm, h->n_wk.p, h->n_k.p, h->beta, h->phiT.p,
+                                  h->partial.p, h->row0, h->row1, lo, hi, (uint32_t)h->iteration, h->poisson_L, h->stream));
+        h->seg_epoch = ++h->ep[P2P_FLAG_SEG];
+        CK(h, launch_phi_segment_sums_p2p(h->pt, h->seg_epoch, h->dm, h->partial.p, h->seg0, h->seg1, h->stream));
+        h->last_launches += 2;
+        if (ev) { CK(h, cudaEventRecord(ev[0], h->stream)); CK(h, cudaEventRecord(ev[1], h->stream)); }
+    }
+    if (stage < 0 || stage == 1) {
+        double *mean = nullptr;
+        if (phi_mean_buffer(h, accumulate_mean, &mean)) return 1;
+        h->phi_epoch = ++h->ep[P2P_FLAG_PHI];
+        CK(h, launch_phi_normalise_p2p(h->pt, h->seg_epoch, h->phi_epoch, h->dm, h->topic_sum.p, mean, h->row0, h->row1,
+                                       h->poisson_L > 0, h->stream));
+        h->last_launches += 1;
+        if (ev) CK(h, cudaEventRecord(ev[2], h->stream));
+    }
+    if (stage < 0 || stage == 2) {
+        CK(h, launch_p2p_wait(h->pt, P2P_FLAG_PHI, h->phi_epoch, h->stream));
+        h->last_launches += 1;
+        if (step_alias(h)) return 1;
+        if (ev) CK(h, cudaEventRecord(ev[3], h->stream));
+    }
     return 0;
 }
 
 // ev != nullptr: record events after draw+segments, segment all-gather, normalise, Phi all-gather
-int step_phi(ldagpu_handle h, bool accumulate_mean, cudaEvent_t *ev, bool fused_reduce = false)
+int step_phi(ldagpu_handle h, bool accumulate_mean, cudaEvent_t *ev, bool fused_reduce = false, int stage = -1)
 {
-    if (h->p2p) return step_phi_p2p(h, accumulate_mean, ev, fused_reduce);
+    if (h->p2p) return step_phi_p2p(h, accumulate_mean, ev, fused_reduce, stage);
+    if (stage > 0) return 0;
     const uint32_t lo = (uint32_t)h->seed, hi = (uint32_t)(h->seed >> 32);
     CK(h, launch_phi_draw(h->dm, h->n_wk.p, h->beta, h->phiT.p, h->partial.p, h->row0, h->row1, lo, hi,
-                          (uint32_t)h->iteration, h->stream));
+                          (uint32_t)h->iteration, h->poisson_L, h->stream));
     CK(h, launch_phi_segment_sums(h->dm, h->partial.p, h->seg.p, h->seg0, h->seg1, h->stream));
     h->last_launches += 2;
     if (ev) CK(h, cudaEventRecord(ev[0], h->stream));
@@ -370,7 +417,7 @@ int step_phi(ldagpu_handle h, bool accumulate_mean, cudaEvent_t *ev, bool fused_
     if (ev) CK(h, cudaEventRecord(ev[1], h->stream));
     double *mean = nullptr;
     if (phi_mean_buffer(h, accumulate_mean, &mean)) return 1;
-    CK(h, launch_phi_normalise(h->dm, h->seg.p, h->topic_sum.p, h->phiT.p, mean, h->row0, h->row1, h->stream));
+    CK(h, launch_phi_normalise(h->dm, h->seg.p, h->topic_sum.p, h->phiT.p, mean, h->row0, h->row1, h->poisson_L > 0, h->stream));
     h->last_launches += 1;
     if (ev) CK(h, cudaEventRecord(ev[2], h->stream));
     if (h->world > 1) {
@@ -405,21 +452,37 @@ int sync_check(ldagpu_handle h)
     return 0;
 }
 
-// z_out != nullptr: the topic indicators of the last sweep are copied to the host on the copy stream as soon as
-// its z-step has finished, under the count exchange and the Phi draw (the Java shim copies z back into the
-// documents' LabelSequences after every sample() call)
-int run_sweeps(ldagpu_handle h, int32_t n, bool with_phi, int32_t *done, int32_t *z_out = nullptr, uint16_t *z16_out = nullptr)
+// ---- a call of n sweeps in three pieces, so that one caller thread can drive several shards (ldagpu_create_multi):
+// sweeps_prepare, then sweep_enqueue once per sweep (asynchronous), then sweeps_finish (synchronise, timers).
+// z_out / z16_out != nullptr: the topic indicators of the last sweep are copied to the host on the copy stream as
+// soon as its z-step has finished, under the count exchange and the Phi draw (the Java shim copies z back into
+// the documents' LabelSequences after every sample() call)
+struct SweepCall {
+    int32_t n = 0, ran = 0;
+    bool with_phi = true, z_copied = false;
+    int32_t *z_out = nullptr;
+    uint16_t *z16_out = nullptr;
+};
+
+int sweeps_prepare(ldagpu_handle h, SweepCall &c)
 {
     h->last_zk_ms = 0; h->last_call_ms = 0; h->last_zk_launches = 0; h->last_launches = 0;
-    if (done) *done = 0;
-    if (n <= 0) return 0;
-    if (ensure_events(h, (size_t)n * EV_PER_SWEEP)) return 1;
-    if (rendezvous(h)) return 1;
-    int32_t ran = 0;
-    bool z_copied = false;
-    for (int32_t s = 0; s < n; ++s) {
-        if (h->abort_flag.load(std::memory_order_relaxed)) break;
-        cudaEvent_t *ev = h->events.data() + (size_t)s * EV_PER_SWEEP;
+    c.ran = 0; c.z_copied = false;
+    if (c.n <= 0) return 0;
+    return ensure_events(h, (size_t)c.n * EV_PER_SWEEP);
+}
+
+// stage < 0: the whole sweep; otherwise one of SWEEP_STAGES stages (see "Stages" above):
+//   0  [theta] z + counts, topic totals, announce the counts     1, 2  stand-alone count reduce + barrier (z-only sweeps)
+//   3, 4, 5  the three stages of the Phi draw
+enum { SWEEP_STAGES = 1 + (EXCH_STAGES - 1) + PHI_STAGES };
+
+int sweep_enqueue(ldagpu_handle h, SweepCall &c, int stage = -1)
+{
+    const int32_t s = c.ran;
+    const bool all = stage < 0;
+    cudaEvent_t *ev = h->events.data() + (size_t)s * EV_PER_SWEEP;
+    if (all || stage == 0) {
         h->iteration += 1;
         CK(h, cudaEventRecord(ev[0], h->stream));
         // the count rebuild is fused into the z kernel: zero n_wk first (Phi, not n_wk, feeds the z-step)
@@ -431,41 +494,49 @@ int run_sweeps(ldagpu_handle h, int32_t n, bool with_phi, int32_t *done, int32_t
         CK(h, cudaEventRecord(ev[1], h->stream));
         if (step_z(h, true, fuse_theta)) return 1;
         CK(h, cudaEventRecord(ev[2], h->stream));
-        if ((z_out || z16_out) && s == n - 1 && h->dm.N) {
+        if ((c.z_out || c.z16_out) && s == c.n - 1 && h->dm.N) {
             CK(h, cudaEventRecord(h->copy_events[0], h->stream));
             CK(h, cudaStreamWaitEvent(h->copy_stream, h->copy_events[0], 0));
-            if (z16_out) {   // narrow on the device (copy stream, under the Phi draw), half the PCIe bytes
+            if (c.z16_out) {   // narrow on the device (copy stream, under the Phi draw), half the PCIe bytes
                 CK(h, launch_pack16(h->z.p, h->z16.p, h->dm.N, h->sm_count, h->copy_stream));
-                CK(h, cudaMemcpyAsync(z16_out, h->z16.p, sizeof(uint16_t) * (size_t)h->dm.N, cudaMemcpyDeviceToHost, h->copy_stream));
+                CK(h, cudaMemcpyAsync(c.z16_out, h->z16.p, sizeof(uint16_t) * (size_t)h->dm.N, cudaMemcpyDeviceToHost, h->copy_stream));
                 h->last_launches += 1;
             } else {
-                CK(h, cudaMemcpyAsync(z_out, h->z.p, sizeof(int32_t) * (size_t)h->dm.N, cudaMemcpyDeviceToHost, h->copy_stream));
+                CK(h, cudaMemcpyAsync(c.z_out, h->z.p, sizeof(int32_t) * (size_t)h->dm.N, cudaMemcpyDeviceToHost, h->copy_stream));
             }
-            z_copied = true;
+            c.z_copied = true;
         }
         CK(h, launch_topic_totals(h->dm, h->n_wk.p, h->n_k.p, h->stream));
         h->last_launches += 1;
         CK(h, cudaEventRecord(ev[3], h->stream));
-        if (step_counts_exchange(h, with_phi)) return 1;
-        CK(h, cudaEventRecord(ev[4], h->stream));
-        if (with_phi) {
-            bool acc = mean_this_iteration(h);
-            if (step_phi(h, acc, ev + 5, true)) return 1;
-            if (acc) h->n_sampled_phi += 1;   // GGS:168-170
-        } else {
-            for (int i = 5; i < EV_PER_SWEEP; ++i) CK(h, cudaEventRecord(ev[i], h->stream));
-        }
-        ++ran;
+        if (step_counts_exchange(h, c.with_phi, all ? -1 : 0)) return 1;
     }
-    if (!z_copied && h->dm.N) {   // aborted before the last sweep: plain copy of the current z
-        if (z_out) CK(h, cudaMemcpyAsync(z_out, h->z.p, sizeof(int32_t) * (size_t)h->dm.N, cudaMemcpyDeviceToHost, h->stream));
-        if (z16_out) {
+    if (!all && (stage == 1 || stage == 2) && step_counts_exchange(h, c.with_phi, stage)) return 1;
+    if (all || stage == 2) CK(h, cudaEventRecord(ev[4], h->stream));
+    if (c.with_phi) {
+        const bool acc = mean_this_iteration(h);
+        if (all) { if (step_phi(h, acc, ev + 5, true)) return 1; }
+        else if (stage >= 3 && step_phi(h, acc, ev + 5, true, stage - 3)) return 1;
+        if ((all || stage == SWEEP_STAGES - 1) && acc) h->n_sampled_phi += 1;   // GGS:168-170
+    } else if (all || stage == SWEEP_STAGES - 1) {
+        for (int i = 5; i < EV_PER_SWEEP; ++i) CK(h, cudaEventRecord(ev[i], h->stream));
+    }
+    if (all || stage == SWEEP_STAGES - 1) c.ran += 1;
+    return 0;
+}
+
+int sweeps_finish(ldagpu_handle h, SweepCall &c)
+{
+    const int32_t ran = c.ran;
+    if (!c.z_copied && h->dm.N) {   // aborted before the last sweep: plain copy of the current z
+        if (c.z_out) CK(h, cudaMemcpyAsync(c.z_out, h->z.p, sizeof(int32_t) * (size_t)h->dm.N, cudaMemcpyDeviceToHost, h->stream));
+        if (c.z16_out) {
             CK(h, launch_pack16(h->z.p, h->z16.p, h->dm.N, h->sm_count, h->stream));
-            CK(h, cudaMemcpyAsync(z16_out, h->z16.p, sizeof(uint16_t) * (size_t)h->dm.N, cudaMemcpyDeviceToHost, h->stream));
+            CK(h, cudaMemcpyAsync(c.z16_out, h->z16.p, sizeof(uint16_t) * (size_t)h->dm.N, cudaMemcpyDeviceToHost, h->stream));
         }
     }
     if (sync_check(h)) return 1;
-    if (z_copied) CK(h, cudaStreamSynchronize(h->copy_stream));
+    if (c.z_copied) CK(h, cudaStreamSynchronize(h->copy_stream));
     for (int32_t s = 0; s < ran; ++s) {
         cudaEvent_t *ev = h->events.data() + (size_t)s * EV_PER_SWEEP;
         float ms[EV_PER_SWEEP - 1];
@@ -487,7 +558,27 @@ int run_sweeps(ldagpu_handle h, int32_t n, bool with_phi, int32_t *done, int32_t
         CK(h, cudaEventElapsedTime(&total, h->events[0], h->events[(size_t)(ran - 1) * EV_PER_SWEEP + EV_PER_SWEEP - 1]));
         h->last_call_ms = total;
     }
-    if (done) *done = ran;
+    return 0;
+}
+
+int run_sweeps(ldagpu_handle h, int32_t n, bool with_phi, int32_t *done, int32_t *z_out = nullptr, uint16_t *z16_out = nullptr)
+{
+    if (done) *done = 0;
+    SweepCall c;
+    c.n = n; c.with_phi = with_phi; c.z_out = z_out; c.z16_out = z16_out;
+    if (sweeps_prepare(h, c)) return 1;
+    if (n <= 0) return 0;
+    // sharded (one process per GPU): every rank must run the same number of sweeps, or the others would wait for
+    // this one in the exchange -- the ranks agree on the abort flag here, once per call, and a call is short
+    // (the host side caps the sweeps per call); a single GPU looks at its flag before every sweep (UPL:645)
+    int stop = 0;
+    if (rendezvous(h, &stop)) return 1;
+    for (int32_t s = 0; s < n && !stop; ++s) {
+        if (h->world == 1 && h->abort_flag.load(std::memory_order_relaxed)) break;
+        if (sweep_enqueue(h, c)) return 1;
+    }
+    if (sweeps_finish(h, c)) return 1;
+    if (done) *done = c.ran;
     return 0;
 }
 
@@ -651,7 +742,23 @@ double lgamma_stirling_host(double z)
 // =============================================================================================
 extern "C" {
 
-const char *ldagpu_version(void) { return "libldagpu 0.3 (sm_100a; GGS, PCGS, sparse PCGS; peer-memory exchange)"; }
+// single-process multi-GPU layer (end of this file)
+static int multi_destroy(ldagpu_handle P);
+static int multi_init_z(ldagpu_handle P, int32_t seed);
+static int multi_set_z(ldagpu_handle P, const void *z, bool is16, int32_t redraw_phi);
+static int multi_get_z(ldagpu_handle P, void *z, bool is16);
+static int multi_run_sweeps(ldagpu_handle P, int32_t n, bool with_phi, int32_t *done, int32_t *z_out, uint16_t *z16_out);
+static int multi_step(ldagpu_handle P, int what);
+static int multi_get_type_topic_counts(ldagpu_handle P, int32_t *out);
+static int multi_get_doc_topic_counts(ldagpu_handle P, int32_t *out);
+static int multi_set_phi(ldagpu_handle P, const double *phi);
+static int multi_get_phi_mean(ldagpu_handle P, double *phi_mean, int32_t *n_sampled);
+static int multi_theta(ldagpu_handle P, double *theta_out, const double *theta_in);
+static int multi_log_likelihood(ldagpu_handle P, double *ll);
+static int multi_log_posterior(ldagpu_handle P, double *lp);
+enum { MSTEP_THETA = 0, MSTEP_Z = 1, MSTEP_COUNTS = 2, MSTEP_PHI = 3 };
+
+const char *ldagpu_version(void) { return "libldagpu 0.4 (sm_100a; GGS with fused theta, PCGS, sparse PCGS; peer-memory exchange; single-process multi-GPU)"; }
 
 const char *ldagpu_last_error(ldagpu_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -794,6 +901,7 @@ int ldagpu_create(int32_t K, int32_t V, int64_t D, const int64_t *doc_offsets, c
 int ldagpu_destroy(ldagpu_handle h)
 {
     if (!h) return 0;
+    if (h->multi()) return multi_destroy(h);
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
@@ -860,6 +968,7 @@ int ldagpu_comm_init(ldagpu_handle h, int32_t rank, int32_t world, const void *i
 int ldagpu_get_exchange_mode(ldagpu_handle h, int32_t *mode)
 {
     if (!h || !mode) return 1;
+    if (h->multi()) { *mode = 2; return 0; }
     *mode = h->world == 1 ? 0 : (h->p2p ? 2 : 1);
     return 0;
 }
@@ -875,6 +984,7 @@ static int refresh_counts_and_phi(ldagpu_handle h, bool redraw_phi)
 int ldagpu_init_z_java_random(ldagpu_handle h, int32_t seed)
 {
     NEED(h);
+    if (h->multi()) return multi_init_z(h, seed);
     // the stream of nextInt(K) is sequential over the whole corpus: skip the draws of the shards before ours
     JavaRandom r((int64_t)seed);
     for (int64_t i = 0; i < h->dm.token_base; ++i) (void)r.nextInt(h->dm.K);
@@ -891,7 +1001,9 @@ int ldagpu_init_z_java_random(ldagpu_handle h, int32_t seed)
 // one of them is inside [0, K): on an out-of-range indicator the reference throws and keeps its state
 // (UPL:475-481), so do we -- the counts are rebuilt from the untouched z and the call fails.
 // is16: the host buffer holds uint16 (half the PCIe bytes); it is widened on the device.
-static int set_z_impl(ldagpu_handle h, const void *z, bool is16, int32_t redraw_phi)
+// Two pieces, so that one caller thread can drive several shards: set_z_upload enqueues the upload and the counts,
+// set_z_commit (once the range flags of ALL shards are known) commits or restores and enqueues the exchange.
+static int set_z_upload(ldagpu_handle h, const void *z, bool is16)
 {
     const int64_t N = h->dm.N;
     if (!z && N) return h->fail("null z");
@@ -924,44 +1036,76 @@ static int set_z_impl(ldagpu_handle h, const void *z, bool is16, int32_t redraw_
         CK(h, launch_counts_chunk(h->dm, h->tokens.p + o, h->z_stage.p + o, cnt, h->n_wk.p, h->bad.p, h->sm_count, h->stream));
     }
     h->last_launches += nchunk;
-    // sharded: every rank must take the same exit, or the others would wait for this one in the exchange
+    return 0;
+}
+
+// the range flag of this shard (synchronises the shard's stream)
+static int set_z_read_flag(ldagpu_handle h, int *bad)
+{
+    // one process per GPU: every rank must take the same exit, or the others would wait for this one in the exchange
     if (h->world > 1 && h->comm) NK(h, g_nccl.AllReduce(h->bad.p, h->bad.p, 1, ncclInt32, ncclMax, h->comm, h->stream));
-    int bad = 0;
-    CK(h, cudaMemcpyAsync(&bad, h->bad.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(bad, h->bad.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
-    if (!bad) std::swap(h->z.p, h->z_stage.p);   // commit (both buffers have the same size)
-    else CK(h, cudaMemsetAsync(h->n_wk.p, 0, sizeof(int32_t) * h->n_wk.n, h->stream));
-    if (bad) {
-        // keep the previous state: counts from the untouched z, exchanged like any rebuild; Phi was never touched
+    return 0;
+}
+
+// bad == 0: the staged indicators become the resident ones; otherwise the previous state is kept -- the counts are
+// rebuilt from the untouched z and exchanged like any rebuild (Phi was never touched).  Enqueues only.
+// stage < 0: everything; else stage 0 = local part + announce, 1..2 = count reduce + barrier, 3..5 = Phi draw
+static int set_z_commit(ldagpu_handle h, int bad, int32_t redraw_phi, int stage = -1)
+{
+    const bool all = stage < 0;
+    const bool defer = !bad && redraw_phi != 0;
+    if (all || stage == 0) {
         if (rendezvous(h)) return 1;
-        if (step_counts_local(h) || step_counts_exchange(h, false)) return 1;
-        if (sync_check(h)) return 1;
-        return h->fail("topic indicator out of range [0, %d)%s; the previous indicators stay in place", h->dm.K,   // UPL:475-481 throws
-                       h->world > 1 ? " (on this or another rank)" : "");
+        if (bad) {
+            if (step_counts_local(h)) return 1;
+        } else {
+            std::swap(h->z.p, h->z_stage.p);   // both buffers have the same size
+            CK(h, launch_topic_totals(h->dm, h->n_wk.p, h->n_k.p, h->stream));
+            h->last_launches += 1;
+        }
+        if (step_counts_exchange(h, defer, all ? -1 : 0)) return 1;
     }
-    CK(h, launch_topic_totals(h->dm, h->n_wk.p, h->n_k.p, h->stream));
-    h->last_launches += 1;
-    if (rendezvous(h)) return 1;
-    if (step_counts_exchange(h, redraw_phi != 0)) return 1;
-    if (redraw_phi && step_phi(h, false, nullptr, true)) return 1;   // UPL:1842
-    return sync_check(h);
+    if (!all && (stage == 1 || stage == 2) && step_counts_exchange(h, defer, stage)) return 1;
+    if (defer) {   // UPL:1842
+        if (all) { if (step_phi(h, false, nullptr, true)) return 1; }
+        else if (stage >= 3 && step_phi(h, false, nullptr, true, stage - 3)) return 1;
+    }
+    return 0;
+}
+
+static int set_z_fail(ldagpu_handle h, bool sharded)
+{
+    return h->fail("topic indicator out of range [0, %d)%s; the previous indicators stay in place", h->dm.K,   // UPL:475-481 throws
+                   sharded ? " (on this or another shard)" : "");
+}
+
+static int set_z_impl(ldagpu_handle h, const void *z, bool is16, int32_t redraw_phi)
+{
+    int bad = 0;
+    if (set_z_upload(h, z, is16) || set_z_read_flag(h, &bad) || set_z_commit(h, bad, redraw_phi) || sync_check(h)) return 1;
+    return bad ? set_z_fail(h, h->world > 1) : 0;
 }
 
 int ldagpu_set_z(ldagpu_handle h, const int32_t *z, int32_t redraw_phi)
 {
     NEED(h);
+    if (h->multi()) return multi_set_z(h, z, false, redraw_phi);
     return set_z_impl(h, z, false, redraw_phi);
 }
 
 int ldagpu_set_z16(ldagpu_handle h, const uint16_t *z, int32_t redraw_phi)
 {
     NEED(h);
+    if (h->multi()) return multi_set_z(h, z, true, redraw_phi);
     return set_z_impl(h, z, true, redraw_phi);
 }
 
 int ldagpu_get_z16(ldagpu_handle h, uint16_t *z)
 {
     NEED(h);
+    if (h->multi()) return multi_get_z(h, z, true);
     if (h->dm.K > 65536) return h->fail("16-bit topic indicators need K <= 65536");
     if (!h->dm.N) return 0;
     if (!h->z16.p) CK(h, h->z16.alloc((size_t)h->dm.N + 8));
@@ -975,6 +1119,7 @@ int ldagpu_sweep_get_z16(ldagpu_handle h, int32_t n, int32_t *done, uint16_t *z)
     NEED(h);
     if (!z && h->dm.N) return h->fail("null z");
     if (h->dm.K > 65536) return h->fail("16-bit topic indicators need K <= 65536");
+    if (h->multi()) return multi_run_sweeps(h, n, true, done, nullptr, z);
     if (h->dm.N && !h->z16.p) CK(h, h->z16.alloc((size_t)h->dm.N + 8));
     return run_sweeps(h, n, true, done, nullptr, z);
 }
@@ -983,12 +1128,14 @@ int ldagpu_sweep_get_z(ldagpu_handle h, int32_t n, int32_t *done, int32_t *z)
 {
     NEED(h);
     if (!z && h->dm.N) return h->fail("null z");
+    if (h->multi()) return multi_run_sweeps(h, n, true, done, z, nullptr);
     return run_sweeps(h, n, true, done, z);
 }
 
 int ldagpu_get_z(ldagpu_handle h, int32_t *z)
 {
     NEED(h);
+    if (h->multi()) return multi_get_z(h, z, false);
     if (h->dm.N) CK(h, cudaMemcpyAsync(z, h->z.p, sizeof(int32_t) * (size_t)h->dm.N, cudaMemcpyDeviceToHost, h->stream));
     return sync_check(h);
 }
@@ -996,39 +1143,57 @@ int ldagpu_get_z(ldagpu_handle h, int32_t *z)
 int ldagpu_sweep(ldagpu_handle h, int32_t n, int32_t *done)
 {
     NEED(h);
+    if (h->multi()) return multi_run_sweeps(h, n, true, done, nullptr, nullptr);
     return run_sweeps(h, n, true, done);
 }
 
 int ldagpu_sample_z_given_phi(ldagpu_handle h, int32_t n, int32_t *done)
 {
     NEED(h);
+    if (h->multi()) return multi_run_sweeps(h, n, false, done, nullptr, nullptr);
     return run_sweeps(h, n, false, done);
 }
 
-int ldagpu_next_iteration(ldagpu_handle h) { NEED(h); h->iteration += 1; return 0; }
+int ldagpu_next_iteration(ldagpu_handle h)
+{
+    NEED(h);
+    h->iteration += 1;
+    for (ldagpu_handle c : h->shards) c->iteration = h->iteration;
+    return 0;
+}
 int ldagpu_get_iteration(ldagpu_handle h, int32_t *it) { if (!h || !it) return 1; *it = h->iteration; return 0; }
-int ldagpu_set_iteration(ldagpu_handle h, int32_t it) { if (!h) return 1; h->iteration = it; return 0; }
+int ldagpu_set_iteration(ldagpu_handle h, int32_t it)
+{
+    if (!h) return 1;
+    h->iteration = it;
+    for (ldagpu_handle c : h->shards) c->iteration = it;
+    return 0;
+}
 
 int ldagpu_sample_theta(ldagpu_handle h)
 {
     NEED(h);
+    if (h->multi()) return multi_step(h, MSTEP_THETA);
     if (step_theta(h)) return 1;
     return sync_check(h);
 }
 int ldagpu_sample_z(ldagpu_handle h)
 {
     NEED(h);
+    if (h->multi()) return multi_step(h, MSTEP_Z);
     if (step_z(h)) return 1;
     return sync_check(h);
 }
 int ldagpu_rebuild_counts(ldagpu_handle h)
 {
     NEED(h);
+    if (h->multi()) return multi_step(h, MSTEP_COUNTS);
     return refresh_counts_and_phi(h, false);
 }
 int ldagpu_sample_phi(ldagpu_handle h)
 {
     NEED(h);
+    if (h->multi()) return multi_step(h, MSTEP_PHI);
     bool acc = mean_this_iteration(h);
     if (rendezvous(h)) return 1;
     if (step_phi(h, acc, nullptr)) return 1;
@@ -1039,8 +1204,9 @@ int ldagpu_sample_phi(ldagpu_handle h)
 int ldagpu_get_type_topic_counts(ldagpu_handle h, int32_t *out)
 {
     NEED(h);
+    if (h->multi()) return multi_get_type_topic_counts(h, out);
     const size_t cells = (size_t)h->dm.V * h->dm.K;
-    if (h->world > 1) {
+    if (h->world > 1 && h->comm) {
         // every rank holds the global counts of its vocabulary slice only: gather the slices
         const size_t slice = (size_t)(h->dm.Vp / h->world) * h->dm.Ks;
         NK(h, g_nccl.AllGather(h->n_wk.p + (size_t)h->rank * slice, h->n_wk.p, slice, ncclInt32, h->comm, h->stream));
@@ -1056,6 +1222,7 @@ int ldagpu_get_type_topic_counts(ldagpu_handle h, int32_t *out)
 int ldagpu_get_topic_totals(ldagpu_handle h, int32_t *n_k)
 {
     NEED(h);
+    if (h->multi()) return ldagpu_get_topic_totals(h->shards[0], n_k) ? (h->err = h->shards[0]->err, 1) : 0;
     CK(h, cudaMemcpyAsync(n_k, h->n_k.p, sizeof(int32_t) * (size_t)h->dm.K, cudaMemcpyDeviceToHost, h->stream));
     return sync_check(h);
 }
@@ -1063,6 +1230,7 @@ int ldagpu_get_topic_totals(ldagpu_handle h, int32_t *n_k)
 int ldagpu_get_doc_topic_counts(ldagpu_handle h, int32_t *n_dk)
 {
     NEED(h);
+    if (h->multi()) return multi_get_doc_topic_counts(h, n_dk);
     const size_t cells = (size_t)h->dm.D * h->dm.K;
     if (cells == 0) return 0;
     CK(h, h->scratch_i32.alloc(cells));
@@ -1076,6 +1244,7 @@ int ldagpu_get_doc_topic_counts(ldagpu_handle h, int32_t *n_dk)
 int ldagpu_get_phi(ldagpu_handle h, double *phi)
 {
     NEED(h);
+    if (h->multi()) return ldagpu_get_phi(h->shards[0], phi) ? (h->err = h->shards[0]->err, 1) : 0;   // replicated
     const size_t cells = (size_t)h->dm.V * h->dm.K;
     CK(h, h->scratch_f64.alloc(cells));
     CK(h, launch_export_phi(h->dm, h->phiT.p, h->scratch_f64.p, h->stream));
@@ -1088,6 +1257,7 @@ int ldagpu_get_phi(ldagpu_handle h, double *phi)
 int ldagpu_set_phi(ldagpu_handle h, const double *phi)
 {
     NEED(h);
+    if (h->multi()) return multi_set_phi(h, phi);
     const size_t cells = (size_t)h->dm.V * h->dm.K;
     CK(h, h->scratch_f64.alloc(cells));
     CK(h, cudaMemcpyAsync(h->scratch_f64.p, phi, sizeof(double) * cells, cudaMemcpyHostToDevice, h->stream));
@@ -1106,15 +1276,28 @@ int ldagpu_set_phi_mean_schedule(ldagpu_handle h, int32_t burn_in, int32_t thin)
     if (!h) return 1;
     h->mean_burn_in = burn_in;
     h->mean_thin = thin < 1 ? 1 : thin;
+    for (ldagpu_handle c : h->shards) { c->mean_burn_in = h->mean_burn_in; c->mean_thin = h->mean_thin; }
+    return 0;
+}
+
+int ldagpu_set_phi_sampler(ldagpu_handle h, int32_t sampler, int32_t alias_poisson_threshold)
+{
+    if (!h) return 1;
+    if (sampler != LDAGPU_PHI_GAMMA && sampler != LDAGPU_PHI_POLYA_URN) return h->fail("unknown Phi sampler");
+    if (sampler == LDAGPU_PHI_POLYA_URN && (alias_poisson_threshold < 1 || alias_poisson_threshold > (1 << 20)))
+        return h->fail("alias_poisson_threshold must be in [1, 2^20]");
+    h->poisson_L = sampler == LDAGPU_PHI_POLYA_URN ? alias_poisson_threshold : 0;
+    for (ldagpu_handle c : h->shards) c->poisson_L = h->poisson_L;
     return 0;
 }
 
 int ldagpu_get_phi_mean(ldagpu_handle h, double *phi_mean, int32_t *n_sampled)
 {
     NEED(h);
+    if (h->multi()) return multi_get_phi_mean(h, phi_mean, n_sampled);
     if (n_sampled) *n_sampled = h->n_sampled_phi;
     if (h->n_sampled_phi == 0 || !h->phi_mean.p) return 0;   // UPL:1955-1958 returns null
-    if (h->world > 1) {
+    if (h->world > 1 && h->comm) {
         const size_t slice = (size_t)(h->dm.Vp / h->world) * h->dm.Ks;
         NK(h, g_nccl.AllGather(h->phi_mean.p + (size_t)h->rank * slice, h->phi_mean.p, slice, ncclDouble, h->comm, h->stream));
     }
@@ -1130,6 +1313,7 @@ int ldagpu_get_phi_mean(ldagpu_handle h, double *phi_mean, int32_t *n_sampled)
 int ldagpu_get_theta(ldagpu_handle h, double *theta)
 {
     NEED(h);
+    if (h->multi()) return multi_theta(h, theta, nullptr);
     if (ensure_theta(h)) return 1;
     const size_t cells = (size_t)h->dm.D * h->dm.K;
     if (cells == 0) return 0;
@@ -1144,6 +1328,7 @@ int ldagpu_get_theta(ldagpu_handle h, double *theta)
 int ldagpu_set_theta(ldagpu_handle h, const double *theta)
 {
     NEED(h);
+    if (h->multi()) return multi_theta(h, nullptr, theta);
     if (ensure_theta(h)) return 1;
     const size_t cells = (size_t)h->dm.D * h->dm.K;
     if (cells == 0) return 0;
@@ -1155,34 +1340,32 @@ int ldagpu_set_theta(ldagpu_handle h, const double *theta)
     return rc;
 }
 
-int ldagpu_log_likelihood(ldagpu_handle h, double *ll)
+// this shard's three partial sums of the log-likelihood into red_out[0..2] (enqueue only): document part, type part
+// over the shard's vocabulary rows, and the number of non-zero cells there
+static int ll_partials(ldagpu_handle h)
 {
-    NEED(h);
     CK(h, launch_ll_doc(h->dm, h->doc_off.p, h->z.p, h->alpha_d.p, h->lgs_alpha.p, h->alpha_sum, h->red.p, N_PARTIALS, h->sm_count,
                          h->stream));
     CK(h, launch_sum_partials(h->red.p, N_PARTIALS, 1, h->red_out.p, h->stream));
     CK(h, launch_ll_type(h->dm, h->n_wk.p, h->beta, h->row0, h->row1, h->red.p, N_PARTIALS, h->stream));
     CK(h, launch_sum_partials(h->red.p, N_PARTIALS, 2, h->red_out.p + 1, h->stream));
-    if (h->world > 1) NK(h, g_nccl.AllReduce(h->red_out.p, h->red_out.p, 3, ncclDouble, ncclSum, h->comm, h->stream));
-    double part[3];
-    std::vector<int32_t> nk((size_t)h->dm.K);
-    CK(h, cudaMemcpyAsync(part, h->red_out.p, sizeof part, cudaMemcpyDeviceToHost, h->stream));
-    CK(h, cudaMemcpyAsync(nk.data(), h->n_k.p, sizeof(int32_t) * nk.size(), cudaMemcpyDeviceToHost, h->stream));
-    if (sync_check(h)) return 1;
-    // UPL:1698,1724-1749: parameter-sum terms, added once
+    return 0;
+}
+
+// UPL:1698,1724-1749: parameter-sum terms, added once
+static double ll_finish(ldagpu_handle h, const double part[3], const std::vector<int32_t> &nk)
+{
     const double bV = h->beta * h->dm.V;
     double v = part[0] + (double)h->D_global * lgamma_stirling_host(h->alpha_sum) + part[1];
     for (int k = 0; k < h->dm.K; ++k) v -= lgamma_stirling_host(bV + nk[(size_t)k]);
     v += lgamma_stirling_host(bV) * h->dm.K;
     v -= lgamma_stirling_host(h->beta) * part[2];
     if (std::isnan(v) || std::isinf(v)) v = 0.0;   // UPL:1730-1755 returns 0
-    *ll = v;
-    return 0;
+    return v;
 }
 
-int ldagpu_log_posterior(ldagpu_handle h, double *lp)
+static int lp_partials(ldagpu_handle h)
 {
-    NEED(h);
     if (ensure_theta(h)) return 1;
     CK(h, launch_lp_tokens(h->dm, h->tokens.p, h->z.p, h->phiT.p, h->red.p, N_PARTIALS, h->stream));
     CK(h, launch_sum_partials(h->red.p, N_PARTIALS, 1, h->red_out.p, h->stream));
@@ -1190,6 +1373,29 @@ int ldagpu_log_posterior(ldagpu_handle h, double *lp)
     CK(h, launch_sum_partials(h->red.p, N_PARTIALS, 1, h->red_out.p + 1, h->stream));
     CK(h, launch_lp_phi(h->dm, h->phiT.p, h->beta, h->row0, h->row1, h->red.p, N_PARTIALS, h->stream));
     CK(h, launch_sum_partials(h->red.p, N_PARTIALS, 1, h->red_out.p + 2, h->stream));
+    return 0;
+}
+
+int ldagpu_log_likelihood(ldagpu_handle h, double *ll)
+{
+    NEED(h);
+    if (h->multi()) return multi_log_likelihood(h, ll);
+    if (ll_partials(h)) return 1;
+    if (h->world > 1) NK(h, g_nccl.AllReduce(h->red_out.p, h->red_out.p, 3, ncclDouble, ncclSum, h->comm, h->stream));
+    double part[3];
+    std::vector<int32_t> nk((size_t)h->dm.K);
+    CK(h, cudaMemcpyAsync(part, h->red_out.p, sizeof part, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(nk.data(), h->n_k.p, sizeof(int32_t) * nk.size(), cudaMemcpyDeviceToHost, h->stream));
+    if (sync_check(h)) return 1;
+    *ll = ll_finish(h, part, nk);
+    return 0;
+}
+
+int ldagpu_log_posterior(ldagpu_handle h, double *lp)
+{
+    NEED(h);
+    if (h->multi()) return multi_log_posterior(h, lp);
+    if (lp_partials(h)) return 1;
     if (h->world > 1) NK(h, g_nccl.AllReduce(h->red_out.p, h->red_out.p, 3, ncclDouble, ncclSum, h->comm, h->stream));
     double part[3];
     CK(h, cudaMemcpyAsync(part, h->red_out.p, sizeof part, cudaMemcpyDeviceToHost, h->stream));
@@ -1198,12 +1404,25 @@ int ldagpu_log_posterior(ldagpu_handle h, double *lp)
     return 0;
 }
 
-int ldagpu_abort(ldagpu_handle h) { if (!h) return 1; h->abort_flag.store(1); return 0; }
+int ldagpu_abort(ldagpu_handle h)
+{
+    if (!h) return 1;
+    h->abort_flag.store(1);
+    for (ldagpu_handle c : h->shards) c->abort_flag.store(1);
+    return 0;
+}
 int ldagpu_get_abort(ldagpu_handle h, int32_t *aborted) { if (!h || !aborted) return 1; *aborted = h->abort_flag.load(); return 0; }
 
 int ldagpu_get_timers(ldagpu_handle h, double *z_ms, double *counts_ms, double *phi_ms, double *comm_ms)
 {
     if (!h) return 1;
+    if (h->multi()) {   // the slowest shard sets the pace of every phase
+        h->t_z = h->t_counts = h->t_phi = h->t_comm = 0;
+        for (ldagpu_handle c : h->shards) {
+            h->t_z = std::max(h->t_z, c->t_z); h->t_counts = std::max(h->t_counts, c->t_counts);
+            h->t_phi = std::max(h->t_phi, c->t_phi); h->t_comm = std::max(h->t_comm, c->t_comm);
+        }
+    }
     if (z_ms) *z_ms = h->t_z;
     if (counts_ms) *counts_ms = h->t_counts;
     if (phi_ms) *phi_ms = h->t_phi;
@@ -1219,6 +1438,457 @@ int ldagpu_get_last_call_stats(ldagpu_handle h, double *call_ms, double *z_kerne
     if (z_kernel_ms) *z_kernel_ms = h->last_zk_ms;
     if (z_kernel_launches) *z_kernel_launches = h->last_zk_launches;
     if (total_launches) *total_launches = h->last_launches;
+    return 0;
+}
+
+// =============================================================================================
+// Single-process multi-GPU: ldagpu_create_multi.
+// The reference drives everything from ONE coordinator thread of one JVM (tui/ParallelLDA.java:173-202,
+// UPL:552-943); so does this layer: the handle it returns owns one shard handle per GPU and every entry point
+// enqueues its work on all shards before it waits for any of them.  The exchange is the peer-memory one
+// (kernels_p2p.cu, kernels_phi.cu) over direct peer pointers (cudaDeviceEnablePeerAccess) -- no IPC, no NCCL,
+// the same fused Phi kernels.  Results are those of the one-process-per-GPU path and of a single GPU, bit for
+// bit: counters are keyed by global indices and the integer sums are order independent.
+// =============================================================================================
+static int multi_fail(ldagpu_handle P, ldagpu_handle c)
+{
+    P->err = c->err;
+    return 1;
+}
+#define MC(P, c, call)                               \
+    do {                                             \
+        cudaSetDevice((c)->device);                  \
+        if (call) return multi_fail(P, c);           \
+    } while (0)
+
+static int multi_sync_all(ldagpu_handle P)
+{
+    for (ldagpu_handle c : P->shards) MC(P, c, sync_check(c));
+    return 0;
+}
+
+static int multi_link_shards(ldagpu_handle P)
+{
+    const int G = (int)P->shards.size();
+    const char *to = getenv("LDAGPU_P2P_TIMEOUT_MS");
+    for (int g = 0; g < G; ++g) {
+        ldagpu_handle c = P->shards[(size_t)g];
+        cudaSetDevice(c->device);
+        c->rank = g; c->world = G; c->comm = nullptr; c->D_global = P->dm.D;
+        const int32_t rows = c->dm.Vp / G;
+        c->row0 = g * rows; c->row1 = c->row0 + rows;
+        c->seg0 = g * (PHI_SEGMENTS / G); c->seg1 = c->seg0 + PHI_SEGMENTS / G;
+        CK(c, c->nk_parts.alloc((size_t)P2P_MAX * c->dm.Ks));
+        CK(c, c->p2p_flags.alloc((size_t)P2P_FLAG_KINDS * P2P_MAX));
+        CK(c, c->p2p_local.alloc((size_t)P2P_FLAG_KINDS + 4));
+        CK(c, cudaMemset(c->nk_parts.p, 0, sizeof(int32_t) * c->nk_parts.n));
+        CK(c, cudaMemset(c->p2p_flags.p, 0, sizeof(uint32_t) * c->p2p_flags.n));
+        CK(c, cudaMemset(c->p2p_local.p, 0, sizeof(uint32_t) * c->p2p_local.n));
+    }
+    for (int g = 0; g < G; ++g) {
+        ldagpu_handle c = P->shards[(size_t)g];
+        PeerTable &pt = c->pt;
+        pt = PeerTable{};
+        pt.rank = g; pt.world = G;
+        pt.done_ctr = c->p2p_local.p;
+        pt.error = reinterpret_cast<int *>(c->p2p_local.p + P2P_FLAG_KINDS);
+        pt.timeout_ns = (unsigned long long)(to ? std::max(1L, atol(to)) : 60000L) * 1000000ull;
+        for (int r = 0; r < G; ++r) {
+            ldagpu_handle o = P->shards[(size_t)r];
+            pt.n_wk[r] = o->n_wk.p; pt.phiT[r] = o->phiT.p; pt.seg[r] = o->seg.p;
+            pt.nk_parts[r] = o->nk_parts.p; pt.flags[r] = o->p2p_flags.p;
+        }
+        c->p2p = true;
+        c->p2p_note = "single process, direct peer pointers";
+    }
+    return 0;
+}
+
+int ldagpu_create_multi(int32_t K, int32_t V, int64_t D, const int64_t *doc_offsets, const int32_t *tokens,
+                        const double *alpha, double beta, uint64_t seed, int32_t scheme, int32_t n_devices,
+                        const int32_t *devices, ldagpu_handle *out)
+{
+    if (out) *out = nullptr;
+    auto bail = [&](const std::string &m) { g_create_error = m; return 1; };
+    if (!out || !doc_offsets || D < 0) return bail("null argument");
+    if (n_devices < 1 || PHI_SEGMENTS % n_devices != 0) return bail("n_devices must be 1, 2, 4 or 8");
+    std::vector<int32_t> dev((size_t)n_devices);
+    for (int g = 0; g < n_devices; ++g) dev[(size_t)g] = devices ? devices[g] : g;
+    if (n_devices == 1) return ldagpu_create(K, V, D, doc_offsets, tokens, alpha, beta, seed, scheme, dev[0], 0, 0, out);
+    const int ndev = ldagpu_device_count();
+    if (ndev == 0) return bail("no CUDA device: libldagpu has no CPU fallback");
+    for (int g = 0; g < n_devices; ++g) {
+        if (dev[(size_t)g] < 0 || dev[(size_t)g] >= ndev) return bail("device ordinal out of range");
+        for (int q = 0; q < g; ++q)
+            if (dev[(size_t)q] == dev[(size_t)g]) return bail("the same device is listed twice");
+    }
+    for (int a = 0; a < n_devices; ++a)
+        for (int b = 0; b < n_devices; ++b) {
+            if (a == b) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, dev[(size_t)a], dev[(size_t)b]) != cudaSuccess || !can) {
+                cudaGetLastError();
+                return bail("no peer access between devices " + std::to_string(dev[(size_t)a]) + " and " + std::to_string(dev[(size_t)b]) +
+                            ": the single-process path needs it (use one process per GPU with ldagpu_comm_init instead)");
+            }
+            cudaSetDevice(dev[(size_t)a]);
+            cudaError_t e = cudaDeviceEnablePeerAccess(dev[(size_t)b], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                cudaGetLastError();
+                return bail(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+            }
+            cudaGetLastError();
+        }
+    // documents shard by TOKEN count into contiguous ranges (north_star)
+    const int64_t N = doc_offsets[D];
+    ldagpu_handle P = new ldagpu_handle_s();
+    P->dm.K = K; P->dm.V = V; P->dm.D = D; P->dm.N = N; P->dm.Ks = K; P->dm.lg = 2;
+    P->scheme = scheme; P->device = dev[0]; P->seed = seed; P->beta = beta; P->world = n_devices;
+    P->shard_doc0.assign((size_t)n_devices + 1, D);
+    P->shard_tok0.assign((size_t)n_devices + 1, N);
+    P->shard_doc0[0] = 0;
+    for (int g = 1; g < n_devices; ++g) {
+        const int64_t target = N / n_devices * g;
+        int64_t d = std::lower_bound(doc_offsets, doc_offsets + D + 1, target) - doc_offsets;
+        d = std::min<int64_t>(std::max<int64_t>(d, P->shard_doc0[(size_t)g - 1]), D);
+        P->shard_doc0[(size_t)g] = d;
+    }
+    for (int g = 0; g <= n_devices; ++g) P->shard_tok0[(size_t)g] = doc_offsets[P->shard_doc0[(size_t)g]];
+    for (int g = 0; g < n_devices; ++g) {
+        const int64_t d0 = P->shard_doc0[(size_t)g], d1 = P->shard_doc0[(size_t)g + 1], t0 = P->shard_tok0[(size_t)g];
+        std::vector<int64_t> loc((size_t)(d1 - d0) + 1);
+        for (int64_t d = d0; d <= d1; ++d) loc[(size_t)(d - d0)] = doc_offsets[d] - t0;
+        ldagpu_handle c = nullptr;
+        if (ldagpu_create(K, V, d1 - d0, loc.data(), tokens ? tokens + t0 : nullptr, alpha, beta, seed, scheme, dev[(size_t)g],
+                          d0, t0, &c)) {
+            multi_destroy(P);
+            return 1;   // g_create_error holds the shard's message
+        }
+        P->shards.push_back(c);
+    }
+    if (multi_link_shards(P)) {
+        for (ldagpu_handle c : P->shards)
+            if (!c->err.empty()) g_create_error = c->err;
+        multi_destroy(P);
+        return 1;
+    }
+    *out = P;
+    return 0;
+}
+
+int ldagpu_get_shards(ldagpu_handle h, int32_t *n_shards, int64_t *first_docs /*[n+1] or null*/)
+{
+    if (!h || !n_shards) return 1;
+    *n_shards = h->multi() ? (int32_t)h->shards.size() : 1;
+    if (first_docs) {
+        if (h->multi()) for (size_t g = 0; g < h->shard_doc0.size(); ++g) first_docs[g] = h->shard_doc0[g];
+        else { first_docs[0] = 0; first_docs[1] = h->dm.D; }
+    }
+    return 0;
+}
+
+static int multi_destroy(ldagpu_handle P)
+{
+    for (ldagpu_handle c : P->shards) {
+        c->p2p = false;     // peer pointers are plain device pointers of the other shards: nothing to unmap
+        ldagpu_destroy(c);
+    }
+    P->shards.clear();
+    delete P;
+    return 0;
+}
+
+// initial z = java.util.Random(seed).nextInt(K) over the WHOLE corpus in document order (UPL:398-406,458-460): one
+// pass, each shard takes its slice; then counts, exchange and the initial Phi on all shards
+static int multi_init_z(ldagpu_handle P, int32_t seed)
+{
+    JavaRandom r((int64_t)seed);
+    std::vector<int32_t> z;
+    for (ldagpu_handle c : P->shards) {
+        z.resize((size_t)c->dm.N);
+        for (int64_t i = 0; i < c->dm.N; ++i) z[(size_t)i] = r.nextInt(c->dm.K);
+        cudaSetDevice(c->device);
+        if (c->dm.N) {
+            CK(P, cudaMemcpyAsync(c->z.p, z.data(), sizeof(int32_t) * z.size(), cudaMemcpyHostToDevice, c->stream));
+            CK(P, cudaStreamSynchronize(c->stream));
+        }
+    }
+    for (ldagpu_handle c : P->shards) MC(P, c, step_counts_local(c) || step_counts_exchange(c, true, 0));
+    for (int st = 0; st < PHI_STAGES; ++st)
+        for (ldagpu_handle c : P->shards) MC(P, c, step_phi(c, false, nullptr, true, st));   // UPL:450
+    return multi_sync_all(P);
+}
+
+static int multi_set_z(ldagpu_handle P, const void *z, bool is16, int32_t redraw_phi)
+{
+    if (!z && P->dm.N) return P->fail("null z");
+    const size_t esz = is16 ? sizeof(uint16_t) : sizeof(int32_t);
+    const int G = (int)P->shards.size();
+    for (int g = 0; g < G; ++g)
+        MC(P, P->shards[(size_t)g], set_z_upload(P->shards[(size_t)g], static_cast<const char *>(z) + (size_t)P->shard_tok0[(size_t)g] * esz, is16));
+    int any = 0;
+    for (ldagpu_handle c : P->shards) {
+        int bad = 0;
+        MC(P, c, set_z_read_flag(c, &bad));
+        any |= bad;
+    }
+    for (int st = 0; st < SWEEP_STAGES; ++st)
+        for (ldagpu_handle c : P->shards) MC(P, c, set_z_commit(c, any, redraw_phi, st));
+    if (multi_sync_all(P)) return 1;
+    return any ? set_z_fail(P, true) : 0;
+}
+
+static int multi_get_z(ldagpu_handle P, void *z, bool is16)
+{
+    const int G = (int)P->shards.size();
+    for (int g = 0; g < G; ++g) {
+        ldagpu_handle c = P->shards[(size_t)g];
+        const int64_t t0 = P->shard_tok0[(size_t)g];
+        if (is16) MC(P, c, ldagpu_get_z16(c, static_cast<uint16_t *>(z) + t0));
+        else MC(P, c, ldagpu_get_z(c, static_cast<int32_t *>(z) + t0));
+    }
+    return 0;
+}
+
+// n sweeps on all shards: sweep s is enqueued on every shard before sweep s + 1 on any (a shard's kernels wait, on
+// the device, for the other shards' kernels of the same sweep); the abort flag is looked at before every sweep
+// and stops all shards at the same one (UPL:645)
+static int multi_run_sweeps(ldagpu_handle P, int32_t n, bool with_phi, int32_t *done, int32_t *z_out, uint16_t *z16_out)
+{
+    if (done) *done = 0;
+    const int G = (int)P->shards.size();
+    std::vector<SweepCall> calls((size_t)G);
+    for (int g = 0; g < G; ++g) {
+        ldagpu_handle c = P->shards[(size_t)g];
+        SweepCall &sc = calls[(size_t)g];
+        sc.n = n; sc.with_phi = with_phi;
+        sc.z_out = z_out ? z_out + P->shard_tok0[(size_t)g] : nullptr;
+        sc.z16_out = z16_out ? z16_out + P->shard_tok0[(size_t)g] : nullptr;
+        cudaSetDevice(c->device);
+        if (sc.z16_out && c->dm.N && !c->z16.p) CK(P, c->z16.alloc((size_t)c->dm.N + 8));
+        MC(P, c, sweeps_prepare(c, sc));
+    }
+    P->last_call_ms = 0; P->last_zk_ms = 0; P->last_zk_launches = 0; P->last_launches = 0;
+    if (n <= 0) return 0;
+    int32_t ran = 0;
+    for (int32_t s = 0; s < n; ++s) {
+        if (P->abort_flag.load(std::memory_order_relaxed)) break;
+        // fault injection for the tests of the bounded waits: LDAGPU_FAULT_STALL_SHARD=g leaves shard g's Phi stages
+        // out, as if its process had died -- the other shards must report a timeout instead of hanging
+        static const int stall = getenv("LDAGPU_FAULT_STALL_SHARD") ? atoi(getenv("LDAGPU_FAULT_STALL_SHARD")) : -1;
+        for (int st = 0; st < SWEEP_STAGES; ++st)
+            for (int g = 0; g < G; ++g) {
+                if (g == stall && st >= 3) { if (st == SWEEP_STAGES - 1) calls[(size_t)g].ran += 1; continue; }
+                MC(P, P->shards[(size_t)g], sweep_enqueue(P->shards[(size_t)g], calls[(size_t)g], st));
+            }
+        ++ran;
+    }
+    for (int g = 0; g < G; ++g) {
+        // a stopped call still owes the caller its z: sweeps_finish copies it when the last sweep did not
+        if (ran < n) calls[(size_t)g].z_copied = false;
+        MC(P, P->shards[(size_t)g], sweeps_finish(P->shards[(size_t)g], calls[(size_t)g]));
+    }
+    P->iteration = P->shards[0]->iteration;
+    for (ldagpu_handle c : P->shards) {
+        P->last_call_ms = std::max(P->last_call_ms, c->last_call_ms);
+        P->last_zk_ms = std::max(P->last_zk_ms, c->last_zk_ms);
+        P->last_zk_launches = std::max(P->last_zk_launches, c->last_zk_launches);
+        P->last_launches += c->last_launches;
+    }
+    if (done) *done = ran;
+    return 0;
+}
+
+static int multi_step(ldagpu_handle P, int what)
+{
+    if (what == MSTEP_THETA) for (ldagpu_handle c : P->shards) MC(P, c, step_theta(c));
+    if (what == MSTEP_Z) for (ldagpu_handle c : P->shards) MC(P, c, step_z(c));
+    if (what == MSTEP_COUNTS) {
+        for (ldagpu_handle c : P->shards) MC(P, c, step_counts_local(c) || step_counts_exchange(c, false, 0));
+        for (int st = 1; st < EXCH_STAGES; ++st)
+            for (ldagpu_handle c : P->shards) MC(P, c, step_counts_exchange(c, false, st));
+    }
+    if (what == MSTEP_PHI) {
+        for (int st = 0; st < PHI_STAGES; ++st)
+            for (ldagpu_handle c : P->shards) MC(P, c, step_phi(c, mean_this_iteration(c), nullptr, false, st));
+        for (ldagpu_handle c : P->shards)
+            if (mean_this_iteration(c)) c->n_sampled_phi += 1;
+    }
+    return multi_sync_all(P);
+}
+
+// every shard holds the global counts (and the Phi-mean sums) of its vocabulary rows only: collect the slices on
+// shard 0 (peer copies) and export from there
+static int multi_gather_rows(ldagpu_handle P, bool mean)
+{
+    ldagpu_handle c0 = P->shards[0];
+    for (size_t g = 1; g < P->shards.size(); ++g) {
+        ldagpu_handle c = P->shards[g];
+        const size_t o = (size_t)c->row0 * c->dm.Ks, cnt = (size_t)(c->row1 - c->row0) * c->dm.Ks;
+        cudaSetDevice(c->device);
+        if (mean) {
+            if (!c->phi_mean.p || !c0->phi_mean.p) continue;
+            CK(P, cudaMemcpyPeerAsync(c0->phi_mean.p + o, c0->device, c->phi_mean.p + o, c->device, sizeof(double) * cnt, c->stream));
+        } else {
+            CK(P, cudaMemcpyPeerAsync(c0->n_wk.p + o, c0->device, c->n_wk.p + o, c->device, sizeof(int32_t) * cnt, c->stream));
+        }
+        CK(P, cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+static int multi_get_type_topic_counts(ldagpu_handle P, int32_t *out)
+{
+    if (multi_gather_rows(P, false)) return 1;
+    MC(P, P->shards[0], ldagpu_get_type_topic_counts(P->shards[0], out));
+    return 0;
+}
+
+static int multi_get_doc_topic_counts(ldagpu_handle P, int32_t *out)
+{
+    for (size_t g = 0; g < P->shards.size(); ++g)
+        MC(P, P->shards[g], ldagpu_get_doc_topic_counts(P->shards[g], out + (size_t)P->shard_doc0[g] * P->dm.K));
+    return 0;
+}
+
+static int multi_set_phi(ldagpu_handle P, const double *phi)
+{
+    for (ldagpu_handle c : P->shards) MC(P, c, ldagpu_set_phi(c, phi));
+    return 0;
+}
+
+static int multi_get_phi_mean(ldagpu_handle P, double *phi_mean, int32_t *n_sampled)
+{
+    if (multi_gather_rows(P, true)) return 1;
+    MC(P, P->shards[0], ldagpu_get_phi_mean(P->shards[0], phi_mean, n_sampled));
+    return 0;
+}
+
+static int multi_theta(ldagpu_handle P, double *theta_out, const double *theta_in)
+{
+    for (size_t g = 0; g < P->shards.size(); ++g) {
+        const size_t o = (size_t)P->shard_doc0[g] * P->dm.K;
+        if (theta_out) MC(P, P->shards[g], ldagpu_get_theta(P->shards[g], theta_out + o));
+        else MC(P, P->shards[g], ldagpu_set_theta(P->shards[g], theta_in + o));
+    }
+    return 0;
+}
+
+static int multi_sum_partials(ldagpu_handle P, bool ll, double part[3])
+{
+    for (ldagpu_handle c : P->shards) MC(P, c, ll ? ll_partials(c) : lp_partials(c));
+    part[0] = part[1] = part[2] = 0.0;
+    for (ldagpu_handle c : P->shards) {   // fixed shard order: the sum is reproducible
+        double q[3];
+        cudaSetDevice(c->device);
+        CK(P, cudaMemcpyAsync(q, c->red_out.p, sizeof q, cudaMemcpyDeviceToHost, c->stream));
+        MC(P, c, sync_check(c));
+        part[0] += q[0]; part[1] += q[1]; part[2] += q[2];
+    }
+    return 0;
+}
+
+static int multi_log_likelihood(ldagpu_handle P, double *ll)
+{
+    double part[3];
+    if (multi_sum_partials(P, true, part)) return 1;
+    ldagpu_handle c0 = P->shards[0];
+    std::vector<int32_t> nk((size_t)c0->dm.K);
+    MC(P, c0, ldagpu_get_topic_totals(c0, nk.data()));
+    *ll = ll_finish(c0, part, nk);
+    return 0;
+}
+
+static int multi_log_posterior(ldagpu_handle P, double *lp)
+{
+    double part[3];
+    if (multi_sum_partials(P, false, part)) return 1;
+    *lp = part[0] + part[1] + part[2];
+    return 0;
+}
+
+// ---- hyper-parameter optimisation hooks (MSL:812-905; UPL:891-894 calls optimizeAlpha / optimizeBeta every
+// hyperparam_optim_interval sweeps).  The fixed-point iteration itself is MALLET's (Dirichlet.learnParameters /
+// learnSymmetricConcentration) and stays on the host; the library supplies the histograms it consumes and takes the
+// new values back.
+static int set_alpha_one(ldagpu_handle h, const double *alpha)
+{
+    const int K = h->dm.K;
+    for (int k = 0; k < K; ++k)
+        if (!(alpha[k] > 0.0)) return h->fail("alpha must be > 0");
+    h->alpha.assign(alpha, alpha + K);
+    h->alpha_sum = 0.0;
+    for (int k = 0; k < K; ++k) h->alpha_sum += alpha[k];
+    std::vector<float> af((size_t)h->dm.Ks, 0.0f);
+    std::vector<double> ad((size_t)h->dm.Ks, 0.0);
+    for (int k = 0; k < K; ++k) { af[(size_t)k] = (float)alpha[k]; ad[(size_t)k] = alpha[k]; }
+    CK(h, cudaMemcpyAsync(h->alpha_f.p, af.data(), sizeof(float) * af.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->alpha_d.p, ad.data(), sizeof(double) * ad.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(h, launch_lgs_table(K, h->alpha_d.p, h->lgs_alpha.p, h->stream));
+    if (step_alias(h)) return 1;   // the sparse scheme's tables are built over alpha_k * phi_kw
+    return sync_check(h);
+}
+
+int ldagpu_set_alpha(ldagpu_handle h, const double *alpha)
+{
+    NEED(h);
+    if (!alpha) return h->fail("null alpha");
+    if (h->multi()) {
+        for (ldagpu_handle c : h->shards) MC(h, c, set_alpha_one(c, alpha));
+        return 0;
+    }
+    return set_alpha_one(h, alpha);
+}
+
+int ldagpu_set_beta(ldagpu_handle h, double beta)
+{
+    if (!h) return 1;
+    if (!(beta > 0.0)) return h->fail("beta must be > 0");
+    h->beta = beta;
+    for (ldagpu_handle c : h->shards) c->beta = beta;
+    return 0;
+}
+
+static int count_histograms_one(ldagpu_handle h, int32_t n_doc_bins, int32_t n_type_bins, DevBuf<unsigned long long> &buf)
+{
+    CK(h, buf.alloc((size_t)std::max(n_doc_bins, 0) + (size_t)std::max(n_type_bins, 0) + 1));
+    CK(h, launch_count_histograms(h->dm, h->doc_off.p, h->z.p, h->n_wk.p, h->row0, h->row1, n_doc_bins > 0 ? buf.p : nullptr,
+                                  n_doc_bins, n_type_bins > 0 ? buf.p + std::max(n_doc_bins, 0) : nullptr, n_type_bins, h->stream));
+    return 0;
+}
+
+int ldagpu_get_count_histograms(ldagpu_handle h, int32_t n_doc_bins, int64_t *doc_topic_hist, int32_t n_type_bins,
+                                int64_t *type_topic_hist)
+{
+    NEED(h);
+    if ((n_doc_bins > 0 && !doc_topic_hist) || (n_type_bins > 0 && !type_topic_hist)) return h->fail("null histogram");
+    const size_t nd = (size_t)std::max(n_doc_bins, 0), nt = (size_t)std::max(n_type_bins, 0);
+    std::vector<unsigned long long> acc(nd + nt + 1, 0ull), tmp(nd + nt + 1);
+    std::vector<ldagpu_handle> parts = h->multi() ? h->shards : std::vector<ldagpu_handle>{h};
+    for (ldagpu_handle c : parts) {
+        DevBuf<unsigned long long> buf;
+        cudaSetDevice(c->device);
+        if (count_histograms_one(c, n_doc_bins, n_type_bins, buf)) { h->err = c->err; return 1; }
+        if (c->world > 1 && c->comm)
+            NK(h, g_nccl.AllReduce(buf.p, buf.p, nd + nt, ncclUint64, ncclSum, c->comm, c->stream));
+        CK(h, cudaMemcpyAsync(tmp.data(), buf.p, sizeof(unsigned long long) * (nd + nt), cudaMemcpyDeviceToHost, c->stream));
+        if (sync_check(c)) { h->err = c->err; buf.release(); return 1; }
+        buf.release();
+        for (size_t i = 0; i < nd + nt; ++i) acc[i] += tmp[i];
+    }
+    const int64_t D_all = h->multi() ? h->dm.D : h->D_global;
+    if (nd) {
+        unsigned long long others = 0;
+        for (size_t i = 1; i < nd; ++i) others += acc[i];
+        acc[0] = (unsigned long long)D_all * (unsigned long long)h->dm.K - others;   // pairs with n_dk = 0
+        for (size_t i = 0; i < nd; ++i) doc_topic_hist[i] = (int64_t)acc[i];
+    }
+    if (nt) {
+        unsigned long long others = 0;
+        for (size_t i = 1; i < nt; ++i) others += acc[nd + i];
+        acc[nd] = (unsigned long long)h->dm.V * (unsigned long long)h->dm.K - others;   // cells with n_wk = 0
+        for (size_t i = 0; i < nt; ++i) type_topic_hist[i] = (int64_t)acc[nd + i];
+    }
     return 0;
 }
 

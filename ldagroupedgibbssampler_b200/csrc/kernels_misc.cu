@@ -346,6 +346,85 @@ cudaError_t launch_sum_partials(const double *partials, int n, int stride, doubl
 }
 
 // ---------------------------------------------------------------------------------------
+// Sufficient statistics of the hyper-parameter optimisation (ModifiedSimpleLDA.java:812-905): how many
+// (document, topic) pairs have n_dk = c, and how many (type, topic) cells have n_wk = c, c >= 1 (bin 0 is
+// filled in by the host: all pairs minus the others).  Counts above the last bin land in the last bin.
+// Equal bins of a warp are merged before the atomic (bins 1 and 2 would otherwise serialise).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void hist_add(unsigned long long *hist, int bin, bool active)
+{
+    const unsigned same = __match_any_sync(FULL, active ? bin : -1 - (int)(threadIdx.x & 31));
+    if (active && (int)(threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&hist[bin], (unsigned long long)__popc(same));
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+hist_doc_topic_kernel(Dims dm, const int64_t *__restrict__ doc_off, const int32_t *__restrict__ z,
+                      unsigned long long *__restrict__ hist, int nbins)
+{
+    extern __shared__ int32_t s_cnt[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    int32_t *cnt = s_cnt + (size_t)warp * dm.Ks;
+    for (int i = lane; i < dm.Ks; i += 32) cnt[i] = 0;
+    __syncwarp();
+    for (int64_t d = (int64_t)blockIdx.x * nwarp + warp; d < dm.D; d += (int64_t)gridDim.x * nwarp) {
+        const int64_t t0 = doc_off[d], t1 = doc_off[d + 1];
+        for (int64_t t = t0 + lane; t < t1; t += 32) atomicAdd(&cnt[z[t]], 1);
+        __syncwarp();
+        for (int64_t tb = t0; tb < t1; tb += 32) {
+            const bool valid = tb + lane < t1;
+            const int k = valid ? z[tb + lane] : -1 - lane;
+            const unsigned same = __match_any_sync(FULL, k);
+            int c = 0;
+            if (valid && lane == __ffs(same) - 1) { c = cnt[k]; cnt[k] = 0; }   // the first token of a topic takes its count
+            __syncwarp();
+            hist_add(hist, c < nbins ? c : nbins - 1, c > 0);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+hist_type_topic_kernel(Dims dm, const int32_t *__restrict__ n_wk, int32_t row0, int32_t row1,
+                       unsigned long long *__restrict__ hist, int nbins)
+{
+    const int64_t cells = (int64_t)(row1 - row0) * dm.Ks;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t rounds = (cells + stride - 1) / stride;
+    for (int64_t r = 0; r < rounds; ++r) {
+        const int64_t i = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        int c = 0;
+        if (i < cells) {
+            const int32_t w = row0 + (int32_t)(i / dm.Ks);
+            const int k = (int)(i % dm.Ks);
+            if (w < dm.V && ttopic(dm, k) < dm.K) c = n_wk[(size_t)w * dm.Ks + k];
+        }
+        hist_add(hist, c < nbins ? c : nbins - 1, c > 0);
+    }
+}
+
+cudaError_t launch_count_histograms(const Dims &dm, const int64_t *doc_off, const int32_t *z, const int32_t *n_wk,
+                                    int32_t row0, int32_t row1, unsigned long long *doc_hist, int n_doc_bins,
+                                    unsigned long long *type_hist, int n_type_bins, cudaStream_t st)
+{
+    cudaError_t e;
+    if (doc_hist && n_doc_bins > 0) {
+        e = cudaMemsetAsync(doc_hist, 0, sizeof(unsigned long long) * (size_t)n_doc_bins, st);
+        if (e != cudaSuccess) return e;
+        int warps = RED_THREADS / 32;
+        while (warps > 1 && sizeof(int32_t) * (size_t)dm.Ks * warps > 200 * 1024) warps /= 2;
+        const size_t smem = sizeof(int32_t) * (size_t)dm.Ks * warps;
+        e = kernel_config(reinterpret_cast<const void *>(hist_doc_topic_kernel), warps * 32, smem, nullptr);
+        if (e != cudaSuccess) return e;
+        if (dm.D > 0) hist_doc_topic_kernel<<<592, warps * 32, smem, st>>>(dm, doc_off, z, doc_hist, n_doc_bins);
+    }
+    if (type_hist && n_type_bins > 0) {
+        e = cudaMemsetAsync(type_hist, 0, sizeof(unsigned long long) * (size_t)n_type_bins, st);
+        if (e != cudaSuccess) return e;
+        if (row1 > row0) hist_type_topic_kernel<<<592, RED_THREADS, 0, st>>>(dm, n_wk, row0, row1, type_hist, n_type_bins);
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
 // log-posterior (UncollapsedParallelLDA.java:1573-1634):
 //   sum_i ln(phi[z_i][w_i] + 1e-12) + sum_d sum_k (n_dk + alpha_k - 1) ln(theta_dk + 1e-12)
 //   + (beta - 1) sum_kv ln(phi_kv + 1e-12)

@@ -37,11 +37,15 @@ constexpr int MAX_GRID_Y = 65535;
 // their Gamma loops -- the reduce-scatter of the sweep happens inside this kernel.  The global counts
 // are written back to the rank's own rows (accessors, log-likelihood), n_k comes from the per-rank
 // totals the peers pushed before they signalled.
-template <bool REDUCE>
+// POLYA (poisson_L > 0): the Poisson Polya-urn draw instead of the Gammas -- X = Poisson(beta + n_wk) per cell
+// (types/PolyaUrnDirichletFixedCoeffPoisson.java:17-44, contract_math.cuh c_poisson), an integer, so most cells
+// of a zero count are exactly 0 and the rows of Phi are sparse.  Same two phases: a zero-count cell is settled by
+// one comparison (u <= exp(-beta)); the rest go through the list.
+template <bool REDUCE, bool POLYA>
 __global__ void __launch_bounds__(PHI_THREADS)
 phi_draw_kernel(PeerTable pt, uint32_t epoch_counts, Dims dm, int32_t *n_wk, int32_t *n_k,
                 double beta, float *__restrict__ phiT, double *__restrict__ partial, int32_t row0, uint32_t seed_lo,
-                uint32_t seed_hi, uint32_t sweep)
+                uint32_t seed_hi, uint32_t sweep, int32_t poisson_L)
 {
     __shared__ int32_t s_n[PHI_ROW_BLOCK][PHI_THREADS];
     __shared__ float s_g[PHI_ROW_BLOCK][PHI_THREADS];
@@ -95,9 +99,10 @@ phi_draw_kernel(PeerTable pt, uint32_t epoch_counts, Dims dm, int32_t *n_wk, int
         }
     }
     __syncthreads();
-    bool boost0;
-    double d0, c0, inva0;
-    gamma_setup<double>(__dadd_rn(beta, 0.0), boost0, d0, c0, inva0);
+    bool boost0 = false;
+    double d0 = 0.0, c0 = 0.0, inva0 = 0.0, p0 = 0.0;
+    if (POLYA) p0 = c_exp_neg<double>(-beta);
+    else gamma_setup<double>(__dadd_rn(beta, 0.0), boost0, d0, c0, inva0);
     // ---- phase 1
     unsigned pend = 0;
     if (col_ok && kt < dm.K) {
@@ -108,10 +113,15 @@ phi_draw_kernel(PeerTable pt, uint32_t epoch_counts, Dims dm, int32_t *n_wk, int
             bool done = false;
             if (s_n[r][tid] == 0) {
                 const unsigned long long cell = (unsigned long long)w * (unsigned long long)dm.K + (unsigned long long)kt;
-                uint4 rnd = philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), sweep, STREAM_PHI << 24, seed_lo, seed_hi);
-                double g;
-                done = gamma_attempt_squeeze<double>(boost0, d0, c0, inva0, rnd, g);
-                if (done) s_g[r][tid] = __double2float_rn(g);
+                if (POLYA) {
+                    uint4 rnd = philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), sweep, STREAM_POISSON << 24, seed_lo, seed_hi);
+                    done = !(uniform52(rnd.x, rnd.y) > p0);   // k = 0: the cell stays exactly zero
+                } else {
+                    uint4 rnd = philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), sweep, STREAM_PHI << 24, seed_lo, seed_hi);
+                    double g;
+                    done = gamma_attempt_squeeze<double>(boost0, d0, c0, inva0, rnd, g);
+                    if (done) s_g[r][tid] = __double2float_rn(g);
+                }
             }
             pend |= (done ? 0u : 1u) << r;
         }
@@ -133,9 +143,14 @@ phi_draw_kernel(PeerTable pt, uint32_t epoch_counts, Dims dm, int32_t *n_wk, int
         const int r = e / PHI_THREADS, col = e % PHI_THREADS;
         const unsigned long long cell = (unsigned long long)(wb + r) * (unsigned long long)dm.K +
                                         (unsigned long long)ttopic(dm, blockIdx.x * PHI_THREADS + col);
-        const double g = c_gamma<double>(__dadd_rn(beta, __int2double_rn(s_n[r][col])), seed_lo, seed_hi, cell,
-                                         sweep, STREAM_PHI);
-        s_g[r][col] = __double2float_rn(g);
+        if (POLYA) {
+            uint4 rnd = philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), sweep, STREAM_POISSON << 24, seed_lo, seed_hi);
+            s_g[r][col] = __int2float_rn(c_poisson(beta, s_n[r][col], poisson_L, p0, rnd));
+        } else {
+            const double g = c_gamma<double>(__dadd_rn(beta, __int2double_rn(s_n[r][col])), seed_lo, seed_hi, cell,
+                                             sweep, STREAM_PHI);
+            s_g[r][col] = __double2float_rn(g);
+        }
         idx = atomicAdd(&s_next, 1);
     }
     __syncthreads();
@@ -153,28 +168,37 @@ phi_draw_kernel(PeerTable pt, uint32_t epoch_counts, Dims dm, int32_t *n_wk, int
 
 cudaError_t launch_phi_draw(const Dims &dm, const int32_t *n_wk, double beta, float *phiT,
                             double *partial, int32_t row0, int32_t row1, uint32_t seed_lo,
-                            uint32_t seed_hi, uint32_t sweep, cudaStream_t st)
+                            uint32_t seed_hi, uint32_t sweep, int32_t poisson_L, cudaStream_t st)
 {
     // grid.y is limited to 65535: very large vocabularies go in slabs of rows
     for (int32_t r0 = row0; r0 < row1; r0 += MAX_GRID_Y * PHI_ROW_BLOCK) {
         const int32_t r1 = r0 + MAX_GRID_Y * PHI_ROW_BLOCK < row1 ? r0 + MAX_GRID_Y * PHI_ROW_BLOCK : row1;
         dim3 grid((dm.Ks + PHI_THREADS - 1) / PHI_THREADS, (r1 - r0) / PHI_ROW_BLOCK);
-        phi_draw_kernel<false><<<grid, PHI_THREADS, 0, st>>>(PeerTable{}, 0u, dm, const_cast<int32_t *>(n_wk), nullptr,
-                                                             beta, phiT, partial, r0, seed_lo, seed_hi, sweep);
+        if (poisson_L > 0)
+            phi_draw_kernel<false, true><<<grid, PHI_THREADS, 0, st>>>(PeerTable{}, 0u, dm, const_cast<int32_t *>(n_wk), nullptr,
+                                                                       beta, phiT, partial, r0, seed_lo, seed_hi, sweep, poisson_L);
+        else
+            phi_draw_kernel<false, false><<<grid, PHI_THREADS, 0, st>>>(PeerTable{}, 0u, dm, const_cast<int32_t *>(n_wk), nullptr,
+                                                                        beta, phiT, partial, r0, seed_lo, seed_hi, sweep, 0);
     }
     return cudaGetLastError();
 }
 
 cudaError_t launch_phi_draw_p2p(const PeerTable &pt, bool reduce_counts, uint32_t epoch_counts, const Dims &dm,
                                 int32_t *n_wk, int32_t *n_k, double beta, float *phiT, double *partial, int32_t row0,
-                                int32_t row1, uint32_t seed_lo, uint32_t seed_hi, uint32_t sweep, cudaStream_t st)
+                                int32_t row1, uint32_t seed_lo, uint32_t seed_hi, uint32_t sweep, int32_t poisson_L,
+                                cudaStream_t st)
 {
-    if (!reduce_counts) return launch_phi_draw(dm, n_wk, beta, phiT, partial, row0, row1, seed_lo, seed_hi, sweep, st);
+    if (!reduce_counts) return launch_phi_draw(dm, n_wk, beta, phiT, partial, row0, row1, seed_lo, seed_hi, sweep, poisson_L, st);
     for (int32_t r0 = row0; r0 < row1; r0 += MAX_GRID_Y * PHI_ROW_BLOCK) {
         const int32_t r1 = r0 + MAX_GRID_Y * PHI_ROW_BLOCK < row1 ? r0 + MAX_GRID_Y * PHI_ROW_BLOCK : row1;
         dim3 grid((dm.Ks + PHI_THREADS - 1) / PHI_THREADS, (r1 - r0) / PHI_ROW_BLOCK);
-        phi_draw_kernel<true><<<grid, PHI_THREADS, 0, st>>>(pt, epoch_counts, dm, n_wk, n_k, beta, phiT, partial, r0,
-                                                            seed_lo, seed_hi, sweep);
+        if (poisson_L > 0)
+            phi_draw_kernel<true, true><<<grid, PHI_THREADS, 0, st>>>(pt, epoch_counts, dm, n_wk, n_k, beta, phiT, partial, r0,
+                                                                      seed_lo, seed_hi, sweep, poisson_L);
+        else
+            phi_draw_kernel<true, false><<<grid, PHI_THREADS, 0, st>>>(pt, epoch_counts, dm, n_wk, n_k, beta, phiT, partial, r0,
+                                                                       seed_lo, seed_hi, sweep, 0);
     }
     return cudaGetLastError();
 }
@@ -240,7 +264,7 @@ template <bool P2P>
 __global__ void __launch_bounds__(PHI_THREADS)
 phi_normalise_kernel(PeerTable pt, uint32_t epoch_seg, uint32_t epoch_phi, Dims dm, const double *__restrict__ seg,
                      double *__restrict__ topic_sum, float *__restrict__ phiT, double *__restrict__ mean_sum,
-                     int32_t row0, int32_t row1)
+                     int32_t row0, int32_t row1, int keep_zeros)
 {
     if (P2P) {
         if (threadIdx.x == 0) p2p_wait_all(pt, P2P_FLAG_SEG, epoch_seg);
@@ -263,7 +287,9 @@ phi_normalise_kernel(PeerTable pt, uint32_t epoch_seg, uint32_t epoch_phi, Dims 
             float v = phiT[idx];
             if (S != 0.0) {
                 v = __double2float_rn(__dmul_rn((double)v, invS));
-                if (v <= 0.0f) v = 0x1p-149f;   // ParallelDirichlet.java:63-65 floors at Double.MIN_VALUE
+                // ParallelDirichlet.java:63-65 floors at Double.MIN_VALUE; "with the Poisson it is allowed to have 0's"
+                // (PolyaUrnDirichletFixedCoeffPoisson.java:36-39)
+                if (v <= 0.0f && !keep_zeros) v = 0x1p-149f;
                 if (!P2P) phiT[idx] = v;
             }
             if (P2P) {
@@ -278,26 +304,26 @@ phi_normalise_kernel(PeerTable pt, uint32_t epoch_seg, uint32_t epoch_phi, Dims 
 }
 
 cudaError_t launch_phi_normalise(const Dims &dm, const double *seg, double *topic_sum, float *phiT,
-                                 double *phi_mean_sum, int32_t row0, int32_t row1, cudaStream_t st)
+                                 double *phi_mean_sum, int32_t row0, int32_t row1, int keep_zeros, cudaStream_t st)
 {
     for (int32_t r0 = row0; r0 < row1; r0 += MAX_GRID_Y * NORM_ROWS) {
         const int32_t r1 = r0 + MAX_GRID_Y * NORM_ROWS < row1 ? r0 + MAX_GRID_Y * NORM_ROWS : row1;
         dim3 grid((dm.Ks + PHI_THREADS - 1) / PHI_THREADS, (r1 - r0 + NORM_ROWS - 1) / NORM_ROWS);
         phi_normalise_kernel<false><<<grid, PHI_THREADS, 0, st>>>(PeerTable{}, 0u, 0u, dm, seg, topic_sum, phiT,
-                                                                  phi_mean_sum, r0, r1);
+                                                                  phi_mean_sum, r0, r1, keep_zeros);
     }
     return cudaGetLastError();
 }
 
 cudaError_t launch_phi_normalise_p2p(const PeerTable &pt, uint32_t epoch_seg, uint32_t epoch_phi, const Dims &dm,
-                                     double *topic_sum, double *phi_mean_sum, int32_t row0, int32_t row1,
+                                     double *topic_sum, double *phi_mean_sum, int32_t row0, int32_t row1, int keep_zeros,
                                      cudaStream_t st)
 {
     if (row1 <= row0) return cudaErrorInvalidValue;   // every rank owns rows
     if ((row1 - row0 + NORM_ROWS - 1) / NORM_ROWS > MAX_GRID_Y) return cudaErrorInvalidConfiguration;   // > 1M rows per rank
     dim3 grid((dm.Ks + PHI_THREADS - 1) / PHI_THREADS, (row1 - row0 + NORM_ROWS - 1) / NORM_ROWS);
     phi_normalise_kernel<true><<<grid, PHI_THREADS, 0, st>>>(pt, epoch_seg, epoch_phi, dm, nullptr, topic_sum, nullptr,
-                                                             phi_mean_sum, row0, row1);
+                                                             phi_mean_sum, row0, row1, keep_zeros);
     return cudaGetLastError();
 }
 

@@ -64,7 +64,9 @@ alias_build_kernel(Dims dm, const float *__restrict__ alpha, const float *__rest
                 const bool valid = i < K;
                 double b = 0.0;
                 if (valid) {
-                    b = __dsub_rn(__ddiv_rn((double)__fmul_rn(alpha[i], ph[i]), norm), k1);
+                    // a type whose Phi column is all zero (possible with the Polya-urn Phi draw) has no prior part:
+                    // its table is never consulted (tn = 0), keep the arithmetic finite
+                    b = norm > 0.0 ? __dsub_rn(__ddiv_rn((double)__fmul_rn(alpha[i], ph[i]), norm), k1) : 0.0;
                     bs[i] = b;
                     tw[i] = AliasSlot{0.0f, i};
                 }
@@ -259,6 +261,12 @@ __device__ __forceinline__ int sparse_draw(const SparseArgs &sa, const int *nz, 
     const float sum = carry;
     const float tot = __fadd_rn(tn, sum);
     slot = -1;
+    if (!(tot > 0.0f)) {
+        // neither the prior nor the document gives this type any mass (its Phi column is all zero over the topics
+        // that matter): the reference draws the topic uniformly (topics/PolyaUrnSpaliasLDA.java:275-277)
+        int i = __float2int_rz(__fmul_rn(u, __int2float_rn(K)));
+        return i > K - 1 ? K - 1 : i;
+    }
     if (u < __fdiv_rn(tn, tot) || nnz == 0) {
         // prior part: alias draw (:265-267, OptimizedGentleAliasMethod.java:100-107)
         const float up = __fadd_rn(u, __fdiv_rn(__fmul_rn(sum, u), tn));

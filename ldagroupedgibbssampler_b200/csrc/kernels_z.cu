@@ -202,24 +202,36 @@ __device__ __forceinline__ void theta_draw_doc(int *cg, unsigned short *plist, c
 
     // ---- phase 1; the cells it leaves open are appended to the pending list as they are found
     //      (ballot + popc, all lanes) and the list is drained whenever another 32 might not fit
+    //      TH_W cells of the lane go through the attempt side by side (gamma_attempt_squeeze_w: independent
+    //      dependency chains in one basic block; the values are those of the scalar attempt)
+    constexpr int TH_W = 2;
 #pragma unroll 1
-    for (int q = 0; q < NT * 4; ++q) {
-        const int p = (q >> 2) * TILE + lane * 4 + (q & 3);
-        const int k = lane * (4 * NT) + q;
-        const bool valid = k < K;
-        bool done = !valid;
-        if (valid && cg[p] == 0) {
-            const float ii_ = tb.i0[p];
+    for (int q = 0; q < NT * 4; q += TH_W) {
+        int p[TH_W];
+        bool valid[TH_W], zero[TH_W], done[TH_W];
+        float dd[TH_W], cc[TH_W], ii[TH_W], gv[TH_W];
+        uint4 rnd[TH_W];
+#pragma unroll
+        for (int w = 0; w < TH_W; ++w) {
+            p[w] = ((q + w) >> 2) * TILE + lane * 4 + ((q + w) & 3);
+            const int k = lane * (4 * NT) + q + w;
+            valid[w] = k < K;
+            zero[w] = valid[w] && cg[p[w]] == 0;
+            dd[w] = tb.d0[p[w]]; cc[w] = tb.c0[p[w]]; ii[w] = tb.i0[p[w]];
             const unsigned long long cell = cell0 + (unsigned long long)k;
-            uint4 w = philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), sweep, STREAM_THETA << 24, rk);
-            float gv;
-            done = gamma_attempt_squeeze<float>(ii_ > 0.0f, tb.d0[p], tb.c0[p], ii_, w, gv);
-            if (done) cg[p] = __float_as_int(gv);
+            rnd[w] = philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), sweep, STREAM_THETA << 24, rk);
         }
-        const unsigned open_mask = __ballot_sync(FULL, !done);
-        if (!done) plist[npend + __popc(open_mask & lt_mask)] = (unsigned short)p;
-        npend += __popc(open_mask);
-        if (npend > TH_PLIST - 32) drain();
+        gamma_attempt_squeeze_w<TH_W>(dd, cc, ii, rnd, done, gv);
+#pragma unroll
+        for (int w = 0; w < TH_W; ++w) {
+            const bool settled = zero[w] && done[w];
+            if (settled) cg[p[w]] = __float_as_int(gv[w]);
+            const bool open = valid[w] && !settled;
+            const unsigned open_mask = __ballot_sync(FULL, open);
+            if (open) plist[npend + __popc(open_mask & lt_mask)] = (unsigned short)p[w];
+            npend += __popc(open_mask);
+        }
+        if (npend > TH_PLIST - 32 * TH_W) drain();
     }
     // ---- phase 2
     if (npend > 0) drain();

@@ -23,7 +23,9 @@ from ._lib import LdaGpuError, ptr
 from .corpus import InstanceList
 
 # gpu_spalias = PCGS with the reference's sparse z-step (scheme "spalias", topics/tui/ParallelLDA.java:401-490)
-SCHEMES = {"gpu_ggs": 0, "gpu_pcgs": 1, "gpu_spalias": 2}
+# gpu_polyaurn = the sparse z-step with the Poisson Polya-urn Phi draw (scheme "polyaurn", ParallelLDA.java:444-446 ->
+# topics/PolyaUrnSpaliasLDA.java)
+SCHEMES = {"gpu_ggs": 0, "gpu_pcgs": 1, "gpu_spalias": 2, "gpu_polyaurn": 2}
 
 
 @dataclass
@@ -53,7 +55,14 @@ class LDAConfiguration:
     max_doc_buf_size: int = 10000         # token buffer of the tokenizers (ParsedLDAConfiguration.java:402-404)
     logging_path: Optional[str] = None    # run directory of the reference's LoggingUtils (util/LoggingUtils.java:43-109):
                                           # log-likelihood.txt / log-posterior.txt are appended there when set
+    save_phi: bool = False                # Phi_KxV_<K>_<V>_<iter>.csv in every diagnostic iteration (UPL:564,806-815)
+    print_ndocs_interval: Sequence[int] = (-1,)   # iteration ranges [a1, b1, a2, b2, ...] for the Theta dump (UPL:555,757-775)
+    print_ndocs_cnt: int = 0              # rows of theta written by that dump (ParsedLDAConfiguration.java:242-244)
+    alias_poisson_threshold: int = 100    # ALIAS_POISSON_DEFAULT_THRESHOLD (types/PoissonFixedCoeffSampler.java:26-51)
+    hyperparam_optim_interval: int = -1   # HYPERPARAM_OPTIM_INTERVAL_DEFAULT: off (UPL:214,891-894)
+    symmetric_alpha: bool = True          # the GPU path keeps alpha symmetric when it is optimised (MSL:812-858)
     gpu_device: int = 0                   # new key
+    gpu_devices: Optional[str] = None     # new key: "0,1,2,3" = shard the corpus over these GPUs from this one process
 
     def getNoTopics(self, default: int = 10) -> int:
         return self.topics
@@ -114,10 +123,94 @@ class LDAConfiguration:
                           ("exec_time", float), ("dataset", str), ("stoplist", str), ("rare_threshold", int),
                           ("keep_numbers", boolean), ("keep_connecting_punctuation", boolean),
                           ("tfidf_vocab_size", int), ("max_doc_buf_size", int), ("logging_path", str),
-                          ("gpu_device", int)):
+                          ("alias_poisson_threshold", int), ("hyperparam_optim_interval", int), ("save_phi", boolean),
+                          ("print_ndocs_interval", lambda v: tuple(int(x) for x in v.replace(";", ",").split(",") if x.strip())),
+                          ("print_ndocs_cnt", int),
+                          ("gpu_device", int), ("gpu_devices", str)):
             if key in vals:
                 setattr(c, key, conv(vals[key].strip()))
         return c
+
+
+def in_range_interval(index: int, range_pairs: Sequence[int]) -> bool:
+    """LDAUtils.inRangeInterval (util/LDAUtils.java:1624-1632)."""
+    if len(range_pairs) < 2:
+        raise ValueError("Range must be at least 2 long!")
+    if len(range_pairs) % 2:
+        raise ValueError("Range must contain an even number of pairs!")
+    return any(range_pairs[i] <= index <= range_pairs[i + 1] for i in range(0, len(range_pairs), 2))
+
+
+def format_double(d: float, no_digits: int = 4) -> str:
+    """LDAUtils.formatDouble (util/LDAUtils.java:1203-1210): ``%.4f``, except that a non-zero value below 1e-4 in
+    magnitude goes through java.text.DecimalFormat("00.###E0") -- two integer digits, at most three fraction digits
+    (HALF_EVEN), the exponent adjusted to match: 1.2345e-5 -> "12.345E-6"."""
+    if d == 0.0 or abs(d) >= 0.0001:
+        return "%.*f" % (no_digits, d)
+    from decimal import ROUND_HALF_EVEN, Decimal
+    x = Decimal(repr(float(abs(d))))
+    e = x.adjusted() - 1                       # mantissa in [10, 100)
+    m = (x.scaleb(-e)).quantize(Decimal("0.001"), rounding=ROUND_HALF_EVEN)
+    if m >= 100:
+        m, e = (m / 10).quantize(Decimal("0.001"), rounding=ROUND_HALF_EVEN), e + 1
+    txt = format(m, "f").rstrip("0").rstrip(".")
+    return ("-" if d < 0 else "") + txt + "E" + str(e)
+
+
+def write_ascii_double_matrix(matrix: np.ndarray, fn: str, sep: str = ","):
+    """LDAUtils.writeASCIIDoubleMatrix (util/LDAUtils.java:1223-1254): one row per line, formatDouble cells."""
+    with open(fn, "w") as f:
+        for row in np.asarray(matrix, np.float64):
+            f.write(sep.join(format_double(float(v)) for v in row) + "\n")
+
+
+def format_top_words_as_csv(top_words: Sequence[Sequence[str]]) -> str:
+    """LDAUtils.formatTopWordsAsCsv (util/LDAUtils.java:1429-1443)."""
+    return "\n".join(",".join(row) for row in top_words)
+
+
+def format_top_words(top_words: Sequence[Sequence[str]]) -> str:
+    """LDAUtils.formatTopWords (util/LDAUtils.java:1445-1460)."""
+    return "\n".join("Topic %d: %s" % (i + 1, " ".join(row)) for i, row in enumerate(top_words))
+
+
+def digamma(z: float) -> float:
+    """Digamma by recurrence up to z >= 6 and the asymptotic series (what MALLET's Dirichlet.digamma does)."""
+    import math
+    psi = 0.0
+    while z < 6.0:
+        psi -= 1.0 / z
+        z += 1.0
+    inv = 1.0 / z
+    inv2 = inv * inv
+    return psi + math.log(z) - 0.5 * inv - inv2 * (1.0 / 12.0 - inv2 * (1.0 / 120.0 - inv2 * (1.0 / 252.0 - inv2 * (
+        1.0 / 240.0 - inv2 * (1.0 / 132.0)))))
+
+
+def learn_symmetric_concentration(count_histogram, observation_lengths, num_dimensions: int, current_value: float,
+                                  iterations: int = 200) -> float:
+    """MALLET 2.0.8 ``Dirichlet.learnSymmetricConcentration`` (the jar is not in the reference tree, pom.xml:130-141;
+    restated from its published source): Minka's fixed point for the concentration alpha_sum of a symmetric
+    Dirichlet-multinomial from two histograms -- ``count_histogram[c]`` = number of (observation, dimension) pairs
+    with count c, ``observation_lengths[n]`` = number of observations of length n.  Called by
+    ModifiedSimpleLDA.optimizeAlpha / optimizeBeta (MSL:847-852,897-901)."""
+    ch = np.asarray(count_histogram, np.float64)
+    ol = np.asarray(observation_lengths, np.float64)
+    largest = int(np.max(np.nonzero(ch)[0])) if np.any(ch[1:] > 0) else 0
+    lengths = np.nonzero(ol)[0]
+    idx = np.arange(1, largest + 1, dtype=np.float64)
+    value = float(current_value)
+    for _ in range(iterations):
+        param = value / num_dimensions
+        # numerator: sum_c hist[c] * sum_{i<c} 1 / (param + i)
+        num = float(np.dot(ch[1:largest + 1], np.cumsum(1.0 / (param + idx - 1.0)))) if largest else 0.0
+        # denominator: sum_n lengths[n] * (digamma(value + n) - digamma(value))
+        base = digamma(value)
+        den = float(sum(ol[n] * (digamma(value + float(n)) - base) for n in lengths if n > 0))
+        if not (num > 0.0 and den > 0.0):
+            break
+        value = param * num / den
+    return value
 
 
 @dataclass
@@ -132,13 +225,18 @@ class TopicAssignment:
 class GpuLDASampler:
     """``LDAGibbsSampler`` + ``LDASamplerWithPhi`` for ``scheme = gpu_ggs | gpu_pcgs``."""
 
-    def __init__(self, config: LDAConfiguration, scheme: Optional[str] = None, device: Optional[int] = None):
+    def __init__(self, config: LDAConfiguration, scheme: Optional[str] = None, device: Optional[int] = None,
+                 devices: Optional[Sequence[int]] = None):
         self._L = _lib.load()
         self.config = config
         self.scheme = scheme or config.getScheme()
         if self.scheme not in SCHEMES:
             raise ValueError(f"unknown scheme {self.scheme!r}: expected one of {sorted(SCHEMES)}")
         self.device = config.gpu_device if device is None else device
+        # several GPUs driven from this one process (ldagpu_create_multi): `devices`, or the gpu_devices key
+        if devices is None and config.gpu_devices:
+            devices = [int(x) for x in str(config.gpu_devices).replace(";", ",").split(",") if x.strip()]
+        self.devices = [int(d) for d in devices] if devices is not None and len(devices) >= 1 else None
         self.numTopics = config.getNoTopics()
         a = config.getAlpha()
         self.alpha = np.full(self.numTopics, a, np.float64)     # MSL:139-143 symmetric alpha
@@ -209,10 +307,21 @@ class GpuLDASampler:
             off, tokens, self._doc_base, self._token_base = take_shard(off, tokens, d0, d1)
         self._doc_off, self._tokens = np.ascontiguousarray(off, np.int64), np.ascontiguousarray(tokens, np.int32)
         self._rank, self._world = rank, world
-        self._ck(self._L.ldagpu_create(self.numTopics, self.numTypes, len(off) - 1, ptr(self._doc_off),
-                                       ptr(self._tokens) if len(tokens) else None, ptr(self.alpha), self.beta,
-                                       self.startSeed & 0xFFFFFFFFFFFFFFFF, SCHEMES[self.scheme], self.device,
-                                       self._doc_base, self._token_base, C.byref(self._h)))
+        if self.devices is not None:
+            if world > 1:
+                raise ValueError("gpu_devices (one process, several GPUs) and world > 1 (one process per GPU) exclude each other")
+            dev = np.ascontiguousarray(self.devices, np.int32)
+            self._ck(self._L.ldagpu_create_multi(self.numTopics, self.numTypes, len(off) - 1, ptr(self._doc_off),
+                                                 ptr(self._tokens) if len(tokens) else None, ptr(self.alpha), self.beta,
+                                                 self.startSeed & 0xFFFFFFFFFFFFFFFF, SCHEMES[self.scheme], len(dev),
+                                                 ptr(dev), C.byref(self._h)))
+        else:
+            self._ck(self._L.ldagpu_create(self.numTopics, self.numTypes, len(off) - 1, ptr(self._doc_off),
+                                           ptr(self._tokens) if len(tokens) else None, ptr(self.alpha), self.beta,
+                                           self.startSeed & 0xFFFFFFFFFFFFFFFF, SCHEMES[self.scheme], self.device,
+                                           self._doc_base, self._token_base, C.byref(self._h)))
+        if self.scheme == "gpu_polyaurn":
+            self._ck(self._L.ldagpu_set_phi_sampler(self._h, 1, int(self.config.alias_poisson_threshold)))
         if world > 1:
             if comm_id is None:
                 raise ValueError("world > 1 needs the 128-byte communicator id (GpuLDASampler.make_comm_id on rank 0)")
@@ -269,6 +378,9 @@ class GpuLDASampler:
             n = min(step, iterations - done_total)
             if cfg.compute_likelihood:   # keep the log-likelihood on its topic_interval grid
                 n = min(n, max(1, cfg.topic_interval) - done_total % max(1, cfg.topic_interval))
+            if cfg.hyperparam_optim_interval > 1:   # stop where alpha and beta are re-estimated (UPL:891-894)
+                it = self.getCurrentIteration()
+                n = min(n, cfg.hyperparam_optim_interval - it % cfg.hyperparam_optim_interval)
             if cfg.start_diagnostic > 0:
                 # the diagnostic block runs after every sweep from start_diagnostic on (UPL:707-823)
                 it = self.getCurrentIteration()
@@ -289,11 +401,15 @@ class GpuLDASampler:
             done_total += done
             if cfg.start_diagnostic > 0 and done == n and self.getCurrentIteration() >= cfg.start_diagnostic:
                 self._log_posterior_to_file(self.computeLogPosterior())                       # UPL:820-821
+                self._diagnostic_dumps(theta_ready=True)                                      # UPL:757-775,806-815
             if cfg.compute_likelihood and done == n and done_total % max(1, cfg.topic_interval) == 0:
                 self.loglikelihood.append(self.modelLogLikelihood())
                 self._log_likelihood_to_file(self.loglikelihood[-1])                          # UPL:846-850
             if done < n:
                 break
+            if cfg.hyperparam_optim_interval > 1 and self.getCurrentIteration() % cfg.hyperparam_optim_interval == 0:
+                self.optimizeAlpha()
+                self.optimizeBeta()
             if (sum(self.getTimers()) - t_start) / 1000.0 >= cfg.exec_time > 0:        # UPL:926-928
                 break
         if z_out is not None and not z_filled:
@@ -464,6 +580,77 @@ class GpuLDASampler:
         v = C.c_double(0)
         self._ck(self._L.ldagpu_log_posterior(self._h, C.byref(v)))
         return v.value
+
+    # ---- outputs of the driver and of the diagnostic block ---------------------------------------------------------
+    def getTopWordIndices(self, noWords: int) -> np.ndarray:
+        """LDAUtils.getTopWordIndices (util/LDAUtils.java:896-912): per topic the types sorted by n_wk descending (a
+        stable sort: ties keep the type order, as Arrays.sort on IDSorter objects does): int[K][noWords]."""
+        if noWords > self.numTypes:
+            raise ValueError(f"Asked for more words ({noWords}) than there are types (unique words = noTypes = {self.numTypes}).")
+        n_wk = self.getTypeTopicMatrix()
+        return np.stack([np.argsort(-n_wk[:, k], kind="stable")[:noWords] for k in range(self.numTopics)]).astype(np.int32)
+
+    def getTopWords(self, noWords: int) -> List[List[str]]:
+        """LDAUtils.getTopWords (util/LDAUtils.java:874-894) on this sampler's counts and alphabet."""
+        alph = self.getAlphabet()
+        return [[str(alph.lookupObject(int(t))) for t in row] for row in self.getTopWordIndices(noWords)]
+
+    def writeTopWords(self, path: str, noWords: int = 20):
+        """TopWords.txt as the driver writes it (topics/tui/ParallelLDA.java:56,268-282)."""
+        with open(path, "w") as f:
+            f.write(format_top_words_as_csv(self.getTopWords(min(noWords, self.numTypes))) + "\n")
+
+    def _diagnostic_dumps(self, theta_ready: bool):
+        """The file outputs of the diagnostic block (UPL:707-823) besides log-posterior.txt: Theta_DxK_<n>_<K>_<iter>.csv
+        for iterations inside print_ndocs_interval (first print_ndocs_cnt documents, UPL:757-775) and
+        Phi_KxV_<K>_<V>_<iter>.csv when save_phi is set (UPL:806-815), both under <logging_path>/ascii (UPL:572-574)."""
+        cfg = self.config
+        if not cfg.logging_path or self._rank != 0:
+            return
+        it = self.getCurrentIteration()
+        asc = os.path.join(cfg.logging_path, "ascii")
+        want_theta = len(cfg.print_ndocs_interval) > 1 and in_range_interval(it, cfg.print_ndocs_interval)
+        if want_theta or cfg.save_phi:
+            os.makedirs(asc, exist_ok=True)
+        if want_theta:
+            if not theta_ready and self.scheme != "gpu_ggs":
+                self._ck(self._L.ldagpu_sample_theta(self._h))
+            theta = self.getTheta()
+            n = cfg.print_ndocs_cnt
+            rows = theta[:n] if len(theta) > n else theta
+            write_ascii_double_matrix(rows, os.path.join(asc, "Theta_DxK_%d_%d_%05d.csv" % (n, self.numTopics, it)))
+        if cfg.save_phi:
+            write_ascii_double_matrix(self.getPhi(), os.path.join(asc, "Phi_KxV_%d_%d_%05d.csv" % (self.numTopics, self.numTypes, it)))
+
+    # ---- hyper-parameter optimisation (MSL:812-905; UPL:891-894 every hyperparam_optim_interval sweeps) -----------
+    def _count_histograms(self):
+        """(doc_topic_hist, type_topic_hist, doc_length_hist, topic_size_hist) -- the sufficient statistics of
+        MSL:815-846 (documentTopicHistogram merged over topics, the symmetric case), :860-875, :419-431, :877-889."""
+        self._need()
+        lens = np.diff(self._doc_off)
+        max_len = int(lens.max()) if len(lens) else 0
+        type_freq = np.bincount(self._tokens, minlength=self.numTypes)
+        max_type = int(type_freq.max()) if len(type_freq) else 0
+        dh = np.zeros(max_len + 1, np.int64)
+        th = np.zeros(max_type + 1, np.int64)
+        self._ck(self._L.ldagpu_get_count_histograms(self._h, len(dh), ptr(dh), len(th), ptr(th)))
+        n_k = self.getTopicTotals()
+        return dh, th, np.bincount(lens, minlength=max_len + 1), np.bincount(n_k, minlength=int(n_k.max()) + 1)
+
+    def optimizeAlpha(self):
+        """MSL:812-858 for a symmetric alpha (the GPU path keeps alpha symmetric): alphaSum by the fixed point over
+        the histogram of n_dk, then alpha_k = alphaSum / K, pushed into the library."""
+        dh, _, doc_len_hist, _ = self._count_histograms()
+        alpha_sum = learn_symmetric_concentration(dh, doc_len_hist, self.numTopics, float(self.alpha.sum()))
+        self.alpha = np.full(self.numTopics, alpha_sum / self.numTopics, np.float64)
+        self._ck(self._L.ldagpu_set_alpha(self._h, ptr(self.alpha)))
+
+    def optimizeBeta(self):
+        """MSL:860-905: betaSum by the same fixed point over the histogram of n_wk and of the topic sizes."""
+        _, th, _, topic_size_hist = self._count_histograms()
+        beta_sum = learn_symmetric_concentration(th, topic_size_hist, self.numTypes, self.beta * self.numTypes)
+        self.beta = beta_sum / self.numTypes
+        self._ck(self._L.ldagpu_set_beta(self._h, self.beta))
 
     def _log_posterior_to_file(self, lp: float):
         """util/LDAUtils.java:955-968: `iteration<TAB>logPosterior (6 decimals)<TAB>millis` appended to log-posterior.txt"""

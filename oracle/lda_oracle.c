@@ -733,6 +733,107 @@ void oracle_phi_contract(int32_t V, int32_t K, const int32_t *n_wk, double beta,
     free(partial);
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Poisson Polya-urn Phi draw.  Reference: topics/PolyaUrnSpaliasLDA.java:495-507 ->
+ * types/PolyaUrnDirichletFixedCoeffPoisson.java:17-44: X_w = Poisson(beta + n_wk) through
+ * types/PoissonFixedCoeffSampler.java:45-51 (alias table over the pmf truncated to [0, 2L) for n < L, the normal
+ * approximation of types/PolyaUrnDirichlet.java:102-107 from L on), phi = X / sum X, zeros allowed.
+ * Contract (contract_math.cuh c_poisson): one Philox block per cell (stream 4); n < L: inversion by sequential
+ * search with one 52-bit uniform; n >= L: floor(sqrt(lambda) x + lambda + 1/2), x = Box-Muller normal, >= 0.
+ * ------------------------------------------------------------------------------------------ */
+static inline double uniform52(uint32_t hi, uint32_t lo)
+{
+    uint64_t n = ((uint64_t)hi << 20) | (uint64_t)(lo >> 12);
+    return ((double)n + 0.5) * 0x1p-52;
+}
+
+static int32_t poisson_contract(double beta, int32_t n, int32_t L, double p0, const uint32_t w[4])
+{
+    double lambda = beta + (double)n;
+    if (n < L) {
+        double u = uniform52(w[0], w[1]);
+        double p = n == 0 ? p0 : c_exp_neg_f64(-lambda);
+        double F = p;
+        int32_t k = 0, kmax = 2 * L - 1;
+        while (u > F && k < kmax) {
+            ++k;
+            p = p * (lambda / (double)k);
+            F = F + p;
+        }
+        return k;
+    }
+    double u1 = ((double)w[0] + 0.5) * 0x1p-32;
+    double x = sqrt(-2.0 * c_ln_f64(u1)) * c_cos2pi_f64(w[1]);
+    double v = fma(sqrt(lambda), x, lambda) + 0.5;
+    double r = floor(v);
+    return r > 0.0 ? (int32_t)r : 0;
+}
+
+/* the same draw with libm (faithful mode): exp / log / cos from glibc, same uniforms */
+static int32_t poisson_faithful(double beta, int32_t n, int32_t L, const uint32_t w[4])
+{
+    double lambda = beta + (double)n;
+    if (n < L) {
+        double u = uniform52(w[0], w[1]);
+        double p = exp(-lambda), F = p;
+        int32_t k = 0, kmax = 2 * L - 1;
+        while (u > F && k < kmax) { ++k; p *= lambda / (double)k; F += p; }
+        return k;
+    }
+    double u1 = ((double)w[0] + 0.5) * 0x1p-32;
+    double x = sqrt(-2.0 * log(u1)) * cos(2.0 * M_PI * f_turn(w[1], 64));
+    long r = lround(floor(sqrt(lambda) * x + lambda + 0.5));
+    return r > 0 ? (int32_t)r : 0;
+}
+
+int32_t oracle_poisson(double beta, int32_t n, int32_t L, uint64_t seed, uint64_t cell, uint32_t sweep, int faithful)
+{
+    uint32_t w[4] = {(uint32_t)cell, (uint32_t)(cell >> 32), sweep, (uint32_t)ORACLE_STREAM_POISSON << 24};
+    philox4x32_10(w, (uint32_t)seed, (uint32_t)(seed >> 32));
+    return faithful ? poisson_faithful(beta, n, L, w) : poisson_contract(beta, n, L, c_exp_neg_f64(-beta), w);
+}
+
+void oracle_phi_polya_contract(int32_t V, int32_t K, const int32_t *n_wk, double beta, int32_t L, uint64_t seed,
+                               uint32_t sweep, float *phiT)
+{
+    const double p0 = c_exp_neg_f64(-beta);
+    double *S = (double *)calloc((size_t)K, sizeof(double));
+    /* the draws are integers: any summation order gives the same (exact) column sums as the kernels' fixed tree */
+    for (int64_t w = 0; w < V; ++w)
+        for (int k = 0; k < K; ++k) {
+            uint64_t cell = (uint64_t)w * (uint64_t)K + (uint64_t)k;
+            uint32_t r[4] = {(uint32_t)cell, (uint32_t)(cell >> 32), sweep, (uint32_t)ORACLE_STREAM_POISSON << 24};
+            philox4x32_10(r, (uint32_t)seed, (uint32_t)(seed >> 32));
+            float x = (float)poisson_contract(beta, n_wk[cell], L, p0, r);
+            phiT[cell] = x;
+            S[k] += (double)x;
+        }
+    for (int64_t w = 0; w < V; ++w)
+        for (int k = 0; k < K; ++k) {
+            if (S[k] == 0.0) continue;   /* a topic that drew nothing keeps its zero row (PolyaUrnDirichletFixedCoeffPoisson.java:33) */
+            phiT[(size_t)w * K + k] = (float)((double)phiT[(size_t)w * K + k] * (1.0 / S[k]));
+        }
+    free(S);
+}
+
+void oracle_phi_polya_faithful(int32_t V, int32_t K, const int32_t *n_wk, double beta, int32_t L, uint64_t seed,
+                               uint32_t sweep, double *phiT)
+{
+    for (int k = 0; k < K; ++k) {   /* per topic, as loopOverTopics: draw the row, sum, divide */
+        double sum = 0.0;
+        for (int64_t w = 0; w < V; ++w) {
+            uint64_t cell = (uint64_t)w * (uint64_t)K + (uint64_t)k;
+            uint32_t r[4] = {(uint32_t)cell, (uint32_t)(cell >> 32), sweep, (uint32_t)ORACLE_STREAM_POISSON << 24};
+            philox4x32_10(r, (uint32_t)seed, (uint32_t)(seed >> 32));
+            double x = (double)poisson_faithful(beta, n_wk[cell], L, r);
+            phiT[cell] = x;
+            sum += x;
+        }
+        if (sum > 0)
+            for (int64_t w = 0; w < V; ++w) phiT[(size_t)w * K + k] /= sum;
+    }
+}
+
 /* Phi draw, faithful: per topic, V Gammas in double, sequential sum, normalise, floor at
  * Double.MIN_VALUE; shape through partition*magnitude (types/ParallelDirichlet.java:46-70). */
 void oracle_phi_faithful(int32_t V, int32_t K, const int32_t *n_wk, double beta, uint64_t seed,

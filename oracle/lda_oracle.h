@@ -32,7 +32,7 @@ extern "C" {
 #endif
 
 enum { ORACLE_GGS = 0, ORACLE_PCGS = 1 };
-enum { ORACLE_STREAM_Z = 1, ORACLE_STREAM_THETA = 2, ORACLE_STREAM_PHI = 3 };
+enum { ORACLE_STREAM_Z = 1, ORACLE_STREAM_THETA = 2, ORACLE_STREAM_PHI = 3, ORACLE_STREAM_POISSON = 4 };
 
 void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 
@@ -91,6 +91,14 @@ void oracle_phi_contract(int32_t V, int32_t K, const int32_t *n_wk, double beta,
                          uint32_t sweep, float *phiT);
 void oracle_phi_faithful(int32_t V, int32_t K, const int32_t *n_wk, double beta, uint64_t seed,
                          uint32_t sweep, double *phiT);
+
+/* Poisson Polya-urn Phi draw; reference: topics/PolyaUrnSpaliasLDA.java:495-507,
+ * types/PolyaUrnDirichletFixedCoeffPoisson.java:17-44, types/PoissonFixedCoeffSampler.java:45-51 (L = alias_poisson_threshold) */
+int32_t oracle_poisson(double beta, int32_t n, int32_t L, uint64_t seed, uint64_t cell, uint32_t sweep, int faithful);
+void oracle_phi_polya_contract(int32_t V, int32_t K, const int32_t *n_wk, double beta, int32_t L, uint64_t seed,
+                               uint32_t sweep, float *phiT);
+void oracle_phi_polya_faithful(int32_t V, int32_t K, const int32_t *n_wk, double beta, int32_t L, uint64_t seed,
+                               uint32_t sweep, double *phiT);
 
 /* MALLET Dirichlet.logGammaStirling (from memory of MALLET 2.0.8) */
 double oracle_log_gamma_stirling(double z);

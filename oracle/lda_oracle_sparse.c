@@ -44,7 +44,8 @@ static void alias_build_contract(int32_t K, const float *alpha_f, const float *p
     for (int i = 0; i < K; ++i) {
         al[i] = i;
         ps[i] = 0.0f;
-        bs[i] = ((double)(alpha_f[i] * phirow[i]) / norm) - k1;
+        /* an all-zero Phi column (Polya-urn Phi draw) has no prior part: the table is never consulted */
+        bs[i] = norm > 0.0 ? ((double)(alpha_f[i] * phirow[i]) / norm) - k1 : 0.0;
         if (bs[i] < 0.0) lows[low++] = i; else highs[high++] = i;
     }
     int steps = 0; /* the reference never increments it (OptimizedGentleAliasMethod.java:67): kept for fidelity */
@@ -164,7 +165,12 @@ void oracle_z_spalias_contract(int64_t D, const int64_t *doc_off, const int32_t 
                 const float tn = type_norm[w];
                 const float tot = tn + sum;
                 int32_t nw;
-                if (u < tn / tot || nnz == 0) {
+                if (!(tot > 0.0f)) {
+                    /* no prior mass and no document mass for this type: uniform topic
+                     * (topics/PolyaUrnSpaliasLDA.java:275-277) */
+                    nw = (int32_t)(u * (float)K);
+                    if (nw > K - 1) nw = K - 1;
+                } else if (u < tn / tot || nnz == 0) {
                     nw = alias_sample_contract(ps + (size_t)w * K, al + (size_t)w * K, K, u + (sum * u) / tn);
                 } else {
                     const float ul = u * tot - tn;
@@ -193,7 +199,7 @@ static void alias_build_faithful(int32_t K, const double *alpha, const double *p
     const double k1 = 1.0 / K;
     for (int i = 0; i < K; ++i) {
         al[i] = i; ps[i] = 0.0;
-        bs[i] = (phirow[i] * alpha[i] / norm) - k1;
+        bs[i] = norm > 0.0 ? (phirow[i] * alpha[i] / norm) - k1 : 0.0;
         if (bs[i] < 0.0) lows[low++] = i; else highs[high++] = i;
     }
     while (low > 0 && high > 0) {
@@ -248,7 +254,10 @@ void oracle_z_spalias_faithful(int64_t D, int32_t V, const int64_t *doc_off, con
                 const double u = (double)z_uniform23(seed, (uint64_t)(token_base + t), sweep);
                 const double u_sigma = u * (tn[w] + sum);
                 int32_t nw;
-                if (u < (tn[w] / (tn[w] + sum)) || nnz == 0) {
+                if (!(tn[w] + sum > 0.0)) {
+                    nw = (int32_t)floor(u * (double)K);   /* PolyaUrnSpaliasLDA.java:275-277 */
+                    if (nw > K - 1) nw = K - 1;
+                } else if (u < (tn[w] / (tn[w] + sum)) || nnz == 0) {
                     double up = u + ((sum * u) / tn[w]);
                     double ups = up * K;
                     int i = (int)ups;

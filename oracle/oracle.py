@@ -16,7 +16,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "liblda_oracle.so")
 
-GGS, PCGS, SPALIAS = 0, 1, 2
+GGS, PCGS, SPALIAS, POLYAURN = 0, 1, 2, 3
 STREAM_Z, STREAM_THETA, STREAM_PHI = 1, 2, 3
 
 
@@ -78,6 +78,9 @@ def lib():
     sig("oracle_z_pcgs_faithful", None, i64, _i64p, _i32p, _i32p, i32, _f64p, _f64p, u64, u32, i64)
     sig("oracle_phi_contract", None, i32, i32, _i32p, f64, u64, u32, _f32p)
     sig("oracle_phi_faithful", None, i32, i32, _i32p, f64, u64, u32, _f64p)
+    sig("oracle_poisson", i32, f64, i32, i32, u64, u64, u32, C.c_int)
+    sig("oracle_phi_polya_contract", None, i32, i32, _i32p, f64, i32, u64, u32, _f32p)
+    sig("oracle_phi_polya_faithful", None, i32, i32, _i32p, f64, i32, u64, u32, _f64p)
     sig("oracle_log_gamma_stirling", f64, f64)
     sig("oracle_log_likelihood", f64, i64, _i64p, _i32p, i32, i32, _i32p, _i32p, _f64p, f64)
     sig("oracle_log_likelihood_lgamma", f64, i64, _i64p, _i32p, i32, i32, _i32p, _i32p, _f64p, f64)
@@ -231,6 +234,24 @@ def phi_faithful(n_wk, beta, seed, sweep):
     return out
 
 
+def phi_polya_contract(n_wk, beta, seed, sweep, L=100):
+    V, K = n_wk.shape
+    out = np.zeros((V, K), np.float32)
+    lib().oracle_phi_polya_contract(V, K, np.ascontiguousarray(n_wk, np.int32), beta, L, seed, sweep, out)
+    return out
+
+
+def phi_polya_faithful(n_wk, beta, seed, sweep, L=100):
+    V, K = n_wk.shape
+    out = np.zeros((V, K), np.float64)
+    lib().oracle_phi_polya_faithful(V, K, np.ascontiguousarray(n_wk, np.int32), beta, L, seed, sweep, out)
+    return out
+
+
+def poisson(beta, n, seed, cell, sweep, L=100, faithful=False):
+    return lib().oracle_poisson(beta, n, L, seed, cell, sweep, 1 if faithful else 0)
+
+
 def log_likelihood(doc_off, z, K, V, n_wk, n_k, alpha, beta, exact_lgamma=False):
     fn = lib().oracle_log_likelihood_lgamma if exact_lgamma else lib().oracle_log_likelihood
     return fn(len(doc_off) - 1, np.ascontiguousarray(doc_off, np.int64),
@@ -255,8 +276,10 @@ def sweeps(mode, scheme, doc_off, tokens, z, V, K, alpha, beta, seed, first_swee
     theta = np.zeros((D, K), ft)
     n_wk = np.zeros((V, K), np.int32)
     n_k = np.zeros(K, np.int32)
-    if scheme == SPALIAS:
-        # same sweep as PCGS with the sparse z-step (the alias tables are rebuilt from every new Phi)
+    if scheme in (SPALIAS, POLYAURN):
+        # same sweep as PCGS with the sparse z-step (the alias tables are rebuilt from every new Phi);
+        # POLYAURN: the rows of Phi come from the Poisson Polya urn instead of the Gammas
+        polya = scheme == POLYAURN
         for s in range(n_sweeps):
             it = first_sweep + s
             if mode == "contract":
@@ -264,7 +287,10 @@ def sweeps(mode, scheme, doc_off, tokens, z, V, K, alpha, beta, seed, first_swee
             else:
                 z = z_spalias_faithful(doc_off, tokens, z, K, alpha, phiT, seed, it)
             n_wk, n_k = rebuild_counts(tokens, z, V, K)
-            phiT = phi_contract(n_wk, beta, seed, it) if mode == "contract" else phi_faithful(n_wk, beta, seed, it)
+            if polya:
+                phiT = phi_polya_contract(n_wk, beta, seed, it) if mode == "contract" else phi_polya_faithful(n_wk, beta, seed, it)
+            else:
+                phiT = phi_contract(n_wk, beta, seed, it) if mode == "contract" else phi_faithful(n_wk, beta, seed, it)
         return dict(z=z, phiT=phiT, theta=theta, n_wk=n_wk, n_k=n_k)
     fn = lib().oracle_sweeps_contract if mode == "contract" else lib().oracle_sweeps_faithful
     fn(scheme, D, V, K, np.ascontiguousarray(doc_off, np.int64),

@@ -204,3 +204,82 @@ def test_two_handles_on_one_device_and_large_smem_paths():
     assert a.getTopicTotals().sum() == len(tokens) and b.getTopicTotals().sum() == len(tokens)
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("K,V,D,mean_len", [(30, 120, 60, 40), (300, 800, 120, 60), (1500, 400, 60, 40)])
+def test_polya_urn_scheme_bit_exact(oracle, K, V, D, mean_len):
+    """scheme gpu_polyaurn (the reference's "polyaurn": topics/PolyaUrnSpaliasLDA.java): the Poisson Polya-urn Phi draw
+    (exact zeros in Phi) and the sparse z-step on top of it, whole sweeps, against the oracle's contract mode."""
+    off, tokens = make_corpus(D, V, mean_len, seed=K + 5, empty_every=11)
+    alpha, beta, seed = 50.0 / K, 0.01, 29
+    s = _sampler("gpu_polyaurn", off, tokens, V, K, alpha, beta, seed)
+    z0 = s.get_z_flat()
+    nw0, _ = oracle.rebuild_counts(tokens, z0, V, K)
+    phi0 = oracle.phi_polya_contract(nw0, beta, seed, 0)
+    got0 = s.getPhi().T.astype(np.float32)
+    assert np.array_equal(got0, phi0)                    # initial Phi: the urn too (UPL:450 -> loopOverTopics override)
+    assert (got0 == 0).mean() > 0.5                      # sparse rows
+    s.sample(3)
+    st = oracle.sweeps("contract", oracle.POLYAURN, off, tokens, z0, V, K, np.full(K, alpha), beta, seed, 1, 3, phi0)
+    assert np.array_equal(s.get_z_flat(), st["z"])
+    assert np.array_equal(s.getTypeTopicMatrix(), st["n_wk"]) and np.array_equal(s.getTopicTotals(), st["n_k"])
+    assert np.array_equal(s.getPhi().T.astype(np.float32), st["phiT"])
+    # against the faithful (libm) urn on the same uniforms
+    pf = oracle.phi_polya_faithful(st["n_wk"], beta, seed, 3)
+    assert np.allclose(s.getPhi().T, pf, rtol=1e-5, atol=1e-12)
+    s.close()
+
+
+def test_polya_urn_large_counts_normal_branch(oracle):
+    """cells with n >= alias_poisson_threshold take the normal approximation (PoissonFixedCoeffSampler.java:45-51)"""
+    import ldagroupedgibbssampler_b200 as L
+    V, K = 6, 4
+    off = np.array([0, 3000, 6000], np.int64)
+    tokens = np.sort(np.concatenate([np.arange(3000) % V, np.arange(3000) % V])).astype(np.int32).reshape(2, 3000)
+    tokens = np.concatenate([np.sort(tokens[0]), np.sort(tokens[1])]).astype(np.int32)
+    cfg = L.LDAConfiguration(scheme="gpu_polyaurn", topics=K, alpha=0.5, beta=0.01, seed=3, exec_time=0,
+                             alias_poisson_threshold=20)
+    s = L.GpuLDASampler(cfg)
+    s.addInstances(L.InstanceList.from_csr(off, tokens, V))
+    z0 = s.get_z_flat()
+    nw0, _ = oracle.rebuild_counts(tokens, z0, V, K)
+    assert nw0.max() > 100
+    assert np.array_equal(s.getPhi().T.astype(np.float32), oracle.phi_polya_contract(nw0, 0.01, 3, 0, L=20))
+    s.close()
+
+
+def test_hyperparameter_hooks(oracle):
+    """MSL:812-905 hooks: the histograms of n_dk and n_wk equal numpy's, set_alpha / set_beta reach the kernels (theta and
+    Phi follow the oracle with the new values), and hyperparam_optim_interval runs the host-side fixed point."""
+    import ldagroupedgibbssampler_b200 as L
+    off, tokens = make_corpus(300, 400, 60, seed=12, empty_every=17)
+    K, V, alpha, beta, seed = 50, 400, 0.2, 0.05, 8
+    s = _sampler("gpu_ggs", off, tokens, V, K, alpha, beta, seed)
+    s.sample(3)
+    dh, th, dl, ts = s._count_histograms()
+    n_dk, n_wk = s.getDocumentTopicMatrix(), s.getTypeTopicMatrix()
+    assert np.array_equal(dh, np.bincount(n_dk.ravel(), minlength=len(dh)))
+    assert np.array_equal(th, np.bincount(n_wk.ravel(), minlength=len(th)))
+    assert dl.sum() == len(off) - 1 and ts.sum() == K
+    # new hyper-parameters reach the kernels
+    new_alpha = np.linspace(0.05, 0.6, K)
+    s._ck(s._L.ldagpu_set_alpha(s._h, new_alpha.ctypes.data))
+    s._ck(s._L.ldagpu_set_beta(s._h, 0.2))
+    z3 = s.get_z_flat()
+    s._step("next_iteration")
+    s._step("sample_theta")
+    assert np.array_equal(s.getTheta().astype(np.float32), oracle.theta_contract(off, z3, K, new_alpha, seed, 4))
+    s._step("sample_phi")
+    assert np.array_equal(s.getPhi().T.astype(np.float32), oracle.phi_contract(n_wk, 0.2, seed, 4))
+    want_ll = oracle.log_likelihood(off, z3, K, V, n_wk, s.getTopicTotals(), new_alpha, 0.2)
+    assert abs(s.modelLogLikelihood() - want_ll) <= 1e-9 * abs(want_ll)
+    s.close()
+    # the optimisation loop itself (symmetric alpha): runs every 2 sweeps, values stay positive and finite and move
+    cfg = L.LDAConfiguration(scheme="gpu_pcgs", topics=K, alpha=alpha, beta=beta, seed=seed, exec_time=0,
+                             hyperparam_optim_interval=2)
+    o = L.GpuLDASampler(cfg)
+    o.addInstances(L.InstanceList.from_csr(off, tokens, V))
+    o.sample(6)
+    assert np.all(np.isfinite(o.alpha)) and np.all(o.alpha > 0) and np.isfinite(o.beta) and o.beta > 0
+    assert abs(o.alpha[0] - alpha) > 1e-6 and np.allclose(o.alpha, o.alpha[0])
+    o.close()

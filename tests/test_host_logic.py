@@ -58,7 +58,7 @@ def test_create_argument_validation():
 def test_unknown_scheme_rejected():
     with pytest.raises(ValueError):
         L.GpuLDASampler(L.LDAConfiguration(scheme="ggs"))    # the Java schemes stay in Java
-    assert set(L.SCHEMES) == {"gpu_ggs", "gpu_pcgs", "gpu_spalias"}
+    assert set(L.SCHEMES) == {"gpu_ggs", "gpu_pcgs", "gpu_spalias", "gpu_polyaurn"}
     assert isinstance(L.createModel(L.LDAConfiguration(scheme="gpu_pcgs", topics=4)), L.GpuLDASampler)
 
 
