@@ -1,7 +1,7 @@
 package cc.mallet.topics;
 
 // Reference-side binding of libldagpu.so (include/ldagpu.h) -- the class a maintainer of
-// clintpgeorge/LDAGroupedGibbsSampler would add for `scheme = gpu_ggs | gpu_pcgs`.
+// clintpgeorge/LDAGroupedGibbsSampler would add for `scheme = gpu_ggs | gpu_pcgs | gpu_spalias | gpu_polyaurn`.
 // NOT compiled in this repository's build image (no JDK there); written against
 //   * the reference's ModifiedSimpleLDA (accessors, data, alphabet; topics/ModifiedSimpleLDA.java)
 //   * the interfaces LDAGibbsSampler (topics/LDAGibbsSampler.java:10-47) and LDASamplerWithPhi
@@ -37,6 +37,12 @@ public class GpuLDASampler extends ModifiedSimpleLDA implements LDAGibbsSampler,
     private static final MethodHandle CREATE = fn("ldagpu_create", FunctionDescriptor.of(JAVA_INT,
             JAVA_INT, JAVA_INT, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS, JAVA_DOUBLE, JAVA_LONG, JAVA_INT, JAVA_INT,
             JAVA_LONG, JAVA_LONG, ADDRESS));
+    // one JVM, several GPUs: the reference has ONE coordinator thread (tui/ParallelLDA.java:173-202 -> UPL:552-943)
+    private static final MethodHandle CREATE_MULTI = fn("ldagpu_create_multi", FunctionDescriptor.of(JAVA_INT,
+            JAVA_INT, JAVA_INT, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS, JAVA_DOUBLE, JAVA_LONG, JAVA_INT, JAVA_INT,
+            ADDRESS, ADDRESS));
+    private static final MethodHandle SET_PHI_SAMPLER = fn("ldagpu_set_phi_sampler", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT));
+    private static final MethodHandle GET_TIMERS = fn("ldagpu_get_timers", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
     private static final MethodHandle DESTROY = fn("ldagpu_destroy", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     private static final MethodHandle LAST_ERROR = fn("ldagpu_last_error", FunctionDescriptor.of(ADDRESS, ADDRESS));
     private static final MethodHandle INIT_Z = fn("ldagpu_init_z_java_random", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
@@ -58,14 +64,37 @@ public class GpuLDASampler extends ModifiedSimpleLDA implements LDAGibbsSampler,
 
     private final Arena arena = Arena.ofShared();
     private MemorySegment handle = MemorySegment.NULL;
-    private final int scheme;             // 0 = gpu_ggs, 1 = gpu_pcgs
+    private final int scheme;             // 0 = gpu_ggs, 1 = gpu_pcgs, 2 = gpu_spalias / gpu_polyaurn (sparse z-step)
+    private final boolean polyaUrn;       // gpu_polyaurn: Poisson Polya-urn Phi draw (topics/PolyaUrnSpaliasLDA.java)
+    private static final int SWEEPS_PER_CALL = 10;   // abort and exec_time are looked at between library calls
     private long[] docOffsets;
     private int numTokens;
     private int noSampledPhi = 0;
 
     public GpuLDASampler(LDAConfiguration config, boolean grouped) {
+        this(config, grouped ? "gpu_ggs" : "gpu_pcgs");
+    }
+
+    /** scheme: gpu_ggs | gpu_pcgs | gpu_spalias | gpu_polyaurn (the new `case` labels of ParallelLDA.createModel) */
+    public GpuLDASampler(LDAConfiguration config, String schemeName) {
         super(config);
-        this.scheme = grouped ? 0 : 1;
+        switch (schemeName) {
+        case "gpu_ggs": scheme = 0; polyaUrn = false; break;
+        case "gpu_pcgs": scheme = 1; polyaUrn = false; break;
+        case "gpu_spalias": scheme = 2; polyaUrn = false; break;
+        case "gpu_polyaurn": scheme = 2; polyaUrn = true; break;
+        default: throw new IllegalArgumentException("unknown GPU scheme " + schemeName);
+        }
+    }
+
+    /** new key `gpu_devices = 0,1,2,3`: shard the corpus over these GPUs from this one JVM (default: gpu_device only) */
+    private int[] gpuDevices() {
+        String v = config.getStringProperty("gpu_devices");
+        if (v == null || v.trim().isEmpty()) return new int[] { config.getIntProperty("gpu_device", 0) };
+        String[] parts = v.split("[,;]");
+        int[] out = new int[parts.length];
+        for (int i = 0; i < parts.length; i++) out[i] = Integer.parseInt(parts[i].trim());
+        return out;
     }
 
     private void ck(int rc) {
@@ -101,11 +130,16 @@ public class GpuLDASampler extends ModifiedSimpleLDA implements LDAGibbsSampler,
         }
         try {
             MemorySegment out = arena.allocate(ADDRESS);
-            ck((int) CREATE.invokeExact(numTopics, numTypes, (long) D,
+            int[] devices = gpuDevices();
+            // the library shards the documents by token count over the devices and exchanges counts / Phi between
+            // them over NVLink peer memory; with one device this is the plain single-GPU handle
+            ck((int) CREATE_MULTI.invokeExact(numTopics, numTypes, (long) D,
                     arena.allocateFrom(JAVA_LONG, docOffsets), arena.allocateFrom(JAVA_INT, tokens),
                     arena.allocateFrom(JAVA_DOUBLE, alpha), beta, (long) getStartSeed(), scheme,
-                    config.getIntProperty("gpu_device", 0), 0L, 0L, out));
+                    devices.length, arena.allocateFrom(JAVA_INT, devices), out));
             handle = out.get(ADDRESS, 0);
+            if (polyaUrn)   // before the first Phi is drawn (UPL:450 -> PolyaUrnSpaliasLDA.loopOverTopics)
+                ck((int) SET_PHI_SAMPLER.invokeExact(handle, 1, config.getAliasPoissonThreshold(LDAConfiguration.ALIAS_POISSON_DEFAULT_THRESHOLD)));
             ck((int) INIT_Z.invokeExact(handle, getStartSeed()));   // Randoms(seed).nextInt(K), UPL:398-406
         } catch (RuntimeException e) {
             throw e;
@@ -149,17 +183,23 @@ public class GpuLDASampler extends ModifiedSimpleLDA implements LDAGibbsSampler,
             catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new IllegalStateException(t); }
         }
         int done = 0;
+        // UPL:577,926-928: stop when zSamplingTimeCum + phiSamplingTimeCum reaches exec_time (default 10 s,
+        // LDAConfiguration.java:35), counted from the start of THIS call; the abort flag is checked as often (UPL:645)
+        double maxExecTimeMillis = config.getMaxExecTimeSeconds(LDAConfiguration.EXEC_TIME_DEFAULT) * 1000.0;
         try (Arena a = Arena.ofConfined()) {
             MemorySegment n = a.allocate(JAVA_INT);
+            double t0 = samplingMillis(a);
             while (done < iterations && !abort) {
-                int step = Math.min(interval, iterations - done);
+                int step = Math.min(Math.min(interval, SWEEPS_PER_CALL), iterations - done);
+                if (config.computeLikelihood()) step = Math.min(step, interval - done % interval);
                 preIteration();
                 ck((int) SWEEP.invokeExact(handle, step, n));
                 done += n.get(JAVA_INT, 0);
                 currentIteration = done;
-                if (config.computeLikelihood()) loglikelihood.add(modelLogLikelihood());
+                if (config.computeLikelihood() && done % interval == 0) loglikelihood.add(modelLogLikelihood());
                 postIteration();
                 if (n.get(JAVA_INT, 0) < step) break;
+                if (maxExecTimeMillis > 0 && samplingMillis(a) - t0 >= maxExecTimeMillis) break;
             }
         } catch (RuntimeException e) {
             throw e;
@@ -168,6 +208,13 @@ public class GpuLDASampler extends ModifiedSimpleLDA implements LDAGibbsSampler,
         }
         pullZ();
         postSample();
+    }
+
+    /** z + count merge + Phi + exchange time so far, in ms (the reference's zSamplingTimeCum + phiSamplingTimeCum) */
+    private double samplingMillis(Arena a) throws Throwable {
+        MemorySegment t = a.allocate(JAVA_DOUBLE, 4);
+        ck((int) GET_TIMERS.invokeExact(handle, t.asSlice(0, 8), t.asSlice(8, 8), t.asSlice(16, 8), t.asSlice(24, 8)));
+        return t.getAtIndex(JAVA_DOUBLE, 0) + t.getAtIndex(JAVA_DOUBLE, 1) + t.getAtIndex(JAVA_DOUBLE, 2) + t.getAtIndex(JAVA_DOUBLE, 3);
     }
 
     @Override

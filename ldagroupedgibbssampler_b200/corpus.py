@@ -267,3 +267,16 @@ def take_shard(doc_offsets: np.ndarray, tokens: np.ndarray, d0: int, d1: int):
     off = np.asarray(doc_offsets, np.int64)
     t0, t1 = int(off[d0]), int(off[d1])
     return (off[d0: d1 + 1] - t0).astype(np.int64), np.ascontiguousarray(tokens[t0:t1], np.int32), d0, t0
+
+
+def write_synthetic_corpus(path: str, D: int, V: int, mean_len: float, seed: int = 20190529, chunk: int = 100000):
+    """Write a synthetic corpus of a BASELINE shape (the generator of ``synth_corpus``) in the reference's
+    ``name<TAB>label<TAB>text`` format (util/LDAUtils.java:233-330) so that the Java driver can read the very corpus the
+    GPU benchmark samples (scripts/run_java_baseline.sh).  Type w becomes the word ``w<id>``."""
+    from ._lib import synth_corpus
+    with open(path, "w") as f:
+        for d0 in range(0, D, chunk):
+            n = min(chunk, D - d0)
+            off, tokens = synth_corpus(n, V, mean_len, seed=seed, doc_first=d0)
+            for d in range(n):
+                f.write("doc%d\tX\t%s\n" % (d0 + d, " ".join("w%d" % t for t in tokens[off[d]:off[d + 1]])))

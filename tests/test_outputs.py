@@ -50,6 +50,7 @@ def test_diagnostic_csv_dumps_and_top_words(tmp_path, oracle):
     off, tokens = make_corpus(40, 60, 30, seed=6)
     K, V = 6, 60
     il = L.InstanceList.from_csr(off, tokens, V)
+    il.alphabet = L.Alphabet("w%d" % i for i in range(V))
     cfg = L.LDAConfiguration(scheme="gpu_ggs", topics=K, alpha=0.5, beta=0.1, seed=4, exec_time=0, start_diagnostic=2,
                              save_phi=True, print_ndocs_interval=(2, 3), print_ndocs_cnt=10, logging_path=str(tmp_path))
     s = L.GpuLDASampler(cfg)
