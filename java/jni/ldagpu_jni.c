@@ -14,6 +14,9 @@
  *       static { System.loadLibrary("ldagpu_jni"); }
  *       static native long   create(int K, int V, long D, long[] docOffsets, int[] tokens, double[] alpha,
  *                                   double beta, long seed, int scheme, int device, long docBase, long tokenBase);
+ *       static native long   createMulti(int K, int V, long D, long[] docOffsets, int[] tokens, double[] alpha,
+ *                                        double beta, long seed, int scheme, int[] devices);   // gpu_devices: one JVM, several GPUs
+ *       static native void   setPhiSampler(long h, int sampler, int aliasPoissonThreshold);     // gpu_polyaurn
  *       static native void   destroy(long h);
  *       static native void   initZJavaRandom(long h, int seed);
  *       static native int    sweepGetZ(long h, int n, int[] z);          // returns the sweeps run
@@ -58,6 +61,35 @@ JNIEXPORT jlong JNICALL CLS(create)(JNIEnv *env, jclass c, jint K, jint V, jlong
     (*env)->ReleaseDoubleArrayElements(env, alpha, al, JNI_ABORT);
     if (rc) { throw_last(env, NULL); return 0; }
     return (jlong)(intptr_t)h;
+}
+
+/* one JVM thread, several GPUs (the reference's coordinator thread, tui/ParallelLDA.java:173-202): the library shards the
+ * corpus over `devices` and exchanges counts / Phi between them over NVLink peer memory */
+JNIEXPORT jlong JNICALL CLS(createMulti)(JNIEnv *env, jclass c, jint K, jint V, jlong D, jlongArray docOffsets,
+                                         jintArray tokens, jdoubleArray alpha, jdouble beta, jlong seed, jint scheme,
+                                         jintArray devices)
+{
+    (void)c;
+    ldagpu_handle h = NULL;
+    jlong *off = (*env)->GetLongArrayElements(env, docOffsets, NULL);
+    jint *tok = (*env)->GetIntArrayElements(env, tokens, NULL);
+    jdouble *al = (*env)->GetDoubleArrayElements(env, alpha, NULL);
+    jint *dev = (*env)->GetIntArrayElements(env, devices, NULL);
+    int rc = ldagpu_create_multi(K, V, D, (const int64_t *)off, (const int32_t *)tok, al, beta, (uint64_t)seed, scheme,
+                                 (*env)->GetArrayLength(env, devices), (const int32_t *)dev, &h);
+    (*env)->ReleaseLongArrayElements(env, docOffsets, off, JNI_ABORT);
+    (*env)->ReleaseIntArrayElements(env, tokens, tok, JNI_ABORT);
+    (*env)->ReleaseDoubleArrayElements(env, alpha, al, JNI_ABORT);
+    (*env)->ReleaseIntArrayElements(env, devices, dev, JNI_ABORT);
+    if (rc) { throw_last(env, NULL); return 0; }
+    return (jlong)(intptr_t)h;
+}
+
+JNIEXPORT void JNICALL CLS(setPhiSampler)(JNIEnv *env, jclass c, jlong h, jint sampler, jint aliasPoissonThreshold)
+{
+    (void)c;
+    if (ldagpu_set_phi_sampler((ldagpu_handle)(intptr_t)h, sampler, aliasPoissonThreshold))
+        throw_last(env, (ldagpu_handle)(intptr_t)h);
 }
 
 JNIEXPORT void JNICALL CLS(destroy)(JNIEnv *env, jclass c, jlong h)

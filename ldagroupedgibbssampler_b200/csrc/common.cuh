@@ -13,7 +13,7 @@ namespace ldagpu {
 
 constexpr int TILE = 128;            // topics per warp tile: lane l owns topics 4l..4l+3 of the tile
 constexpr int MAX_REG_TILES = 8;     // K <= 1024 keeps a whole Phi^T row in registers
-constexpr int GGS_CHUNK_MAX = 256;   // most tokens per GGS work item (documents are split freely; the engine
+constexpr int GGS_CHUNK_MAX = 256;   // most tokens per GGS work item (x4 for corpora beyond ~10^8 tokens per GPU) (documents are split freely; the engine
                                      // picks a multiple of 32 so that every resident warp gets several items)
 constexpr int PHI_ROW_BLOCK = 8;     // words per sequential partial sum of the Phi normaliser
 constexpr int PHI_SEGMENTS = 8;      // vocabulary segments (= max ranks) of the Phi normaliser tree

@@ -130,6 +130,8 @@ struct ldagpu_handle_s {
     DevBuf<int64_t> doc_off, item_begin;
     DevBuf<int32_t> tokens, z, z_stage, n_wk, n_k, item_doc, long_docs, scratch_i32;
     DevBuf<uint16_t> z16;   // 16-bit transport buffer of the topic indicators (ldagpu_set_z16 / ldagpu_sweep_get_z16)
+    struct ZPart { int64_t item0, item1, tok0, tok1; };
+    std::vector<ZPart> z_parts;   // GGS, >= 8 Mi tokens: document-aligned parts of the work items for the streamed read-back of z
     int64_t n_long_docs = 0;   // GGS: documents longer than one work item (their theta is drawn before the z-step)
     DevBuf<float> phiT, theta, alpha_f;
     // sparse scheme: per-type alias tables over alpha_k * phi_kw and the build scratch
@@ -249,13 +251,20 @@ int step_theta(ldagpu_handle h, bool only_long = false)
 }
 
 // fused: the z kernel also accumulates n_wk (which the caller has zeroed)
-int step_z(ldagpu_handle h, bool fused = false, bool fuse_theta = false)
+// part >= 0 (GGS): only the work items of part `part` of h->z_parts -- the last sweep of a call that returns z runs the
+// z-step in parts, so that the read-back of one part overlaps the z-step of the next (sweep_enqueue)
+int step_z(ldagpu_handle h, bool fused = false, bool fuse_theta = false, int part = -1)
 {
-    CK(h, cudaMemsetAsync(h->counter.p, 0, sizeof(unsigned long long), h->stream));
+    unsigned long long *counter = h->counter.p + (part >= 0 ? 1 + part : 0);
+    CK(h, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), h->stream));
     ZArgs a{};
     a.dm = h->dm; a.doc_off = h->doc_off.p; a.tokens = h->tokens.p; a.z = h->z.p; a.phiT = h->phiT.p;
     a.theta = h->theta.p; a.alpha = h->alpha_f.p; a.item_doc = h->item_doc.p; a.item_begin = h->item_begin.p;
-    a.n_items = h->n_items; a.chunk = h->ggs_chunk; a.work_counter = h->counter.p;
+    a.n_items = h->n_items; a.chunk = h->ggs_chunk; a.work_counter = counter;
+    if (part >= 0) {
+        const auto &zp = h->z_parts[(size_t)part];
+        a.item_doc += zp.item0; a.item_begin += zp.item0; a.n_items = zp.item1 - zp.item0;
+    }
     a.n_wk_out = fused ? h->n_wk.p : nullptr;
     a.fuse_theta = fuse_theta ? 1 : 0;
     a.seed_lo = (uint32_t)h->seed; a.seed_hi = (uint32_t)(h->seed >> 32); a.sweep = (uint32_t)h->iteration;
@@ -269,7 +278,7 @@ int step_z(ldagpu_handle h, bool fused = false, bool fuse_theta = false)
     } else {
         CK(h, launch_z_pcgs(a, h->sm_count, h->stream));
     }
-    if (h->n_items) { h->last_launches += 1; h->last_zk_launches += 1; }
+    if (a.n_items) { h->last_launches += 1; h->last_zk_launches += part > 0 ? 0 : 1; }
     return 0;
 }
 
@@ -492,9 +501,28 @@ int sweep_enqueue(ldagpu_handle h, SweepCall &c, int stage = -1)
         const bool fuse_theta = h->scheme == LDAGPU_SCHEME_GGS && fuse_env;
         if (h->scheme == LDAGPU_SCHEME_GGS && step_theta(h, fuse_theta)) return 1;
         CK(h, cudaEventRecord(ev[1], h->stream));
-        if (step_z(h, true, fuse_theta)) return 1;
+        const bool stream_out = (c.z_out || c.z16_out) && s == c.n - 1 && h->scheme == LDAGPU_SCHEME_GGS && h->z_parts.size() > 1;
+        if (stream_out) {
+            // the z-step in document-aligned parts: as soon as a part's indicators are final they are narrowed (16-bit
+            // transport) and copied to the host on the copy stream, under the z-step of the following parts
+            for (size_t p = 0; p < h->z_parts.size(); ++p) {
+                const auto &zp = h->z_parts[p];
+                if (step_z(h, true, fuse_theta, (int)p)) return 1;
+                CK(h, cudaEventRecord(h->copy_events[1 + p], h->stream));
+                CK(h, cudaStreamWaitEvent(h->copy_stream, h->copy_events[1 + p], 0));
+                const int64_t o = zp.tok0, cnt = zp.tok1 - zp.tok0;
+                if (c.z16_out) {
+                    CK(h, launch_pack16(h->z.p + o, h->z16.p + o, cnt, h->sm_count, h->copy_stream));
+                    CK(h, cudaMemcpyAsync(c.z16_out + o, h->z16.p + o, sizeof(uint16_t) * (size_t)cnt, cudaMemcpyDeviceToHost, h->copy_stream));
+                    h->last_launches += 1;
+                } else {
+                    CK(h, cudaMemcpyAsync(c.z_out + o, h->z.p + o, sizeof(int32_t) * (size_t)cnt, cudaMemcpyDeviceToHost, h->copy_stream));
+                }
+            }
+            c.z_copied = true;
+        } else if (step_z(h, true, fuse_theta)) return 1;
         CK(h, cudaEventRecord(ev[2], h->stream));
-        if ((c.z_out || c.z16_out) && s == c.n - 1 && h->dm.N) {
+        if (!stream_out && (c.z_out || c.z16_out) && s == c.n - 1 && h->dm.N) {
             CK(h, cudaEventRecord(h->copy_events[0], h->stream));
             CK(h, cudaStreamWaitEvent(h->copy_stream, h->copy_events[0], 0));
             if (c.z16_out) {   // narrow on the device (copy stream, under the Phi draw), half the PCIe bytes
@@ -594,7 +622,12 @@ int build_items(ldagpu_handle h)
         // item and some with two; smaller chunks give every warp of the persistent grid ~8 items.
         const int64_t resident_warps = (int64_t)h->sm_count * 40;
         int64_t chunk = (h->dm.N / (8 * resident_warps) + 31) / 32 * 32;
-        chunk = std::min<int64_t>(std::max<int64_t>(chunk, 32), GGS_CHUNK_MAX);
+        // a work item that is a whole document draws its theta inside the z kernel; documents longer than the cap
+        // need the stand-alone theta pass first.  The cap grows with the corpus (the tail a long item can leave at
+        // the end of the launch stays below ~1 % of it): 256 tokens up to ~10^8 tokens per GPU, 1024 beyond
+        const int64_t cap = std::min<int64_t>(4 * GGS_CHUNK_MAX,
+                                              std::max<int64_t>(GGS_CHUNK_MAX, h->dm.N / (64 * resident_warps) / 32 * 32));
+        chunk = std::min<int64_t>(std::max<int64_t>(chunk, 32), cap);
         h->ggs_chunk = (int32_t)chunk;
         std::vector<int32_t> long_docs;
         for (int64_t d = 0; d < D; ++d) {
@@ -602,6 +635,25 @@ int build_items(ldagpu_handle h)
             for (int64_t t = off[d]; t < off[d + 1]; t += chunk) {
                 item_doc.push_back((int32_t)d);
                 item_begin.push_back(t);
+            }
+        }
+        // parts for the streamed read-back: 8 document-aligned ranges of about equal token counts
+        h->z_parts.clear();
+        if (h->dm.N >= (8 << 20)) {
+            const int nparts = 8;
+            size_t i0 = 0;
+            for (int p = 0; p < nparts && i0 < item_doc.size(); ++p) {
+                const int64_t target = h->dm.N / nparts * (p + 1);
+                size_t i1 = i0;
+                if (p == nparts - 1) i1 = item_doc.size();
+                else {
+                    while (i1 < item_doc.size() && item_begin[i1] < target) ++i1;
+                    while (i1 < item_doc.size() && i1 > 0 && item_doc[i1] == item_doc[i1 - 1]) ++i1;   // never split a document
+                }
+                if (i1 > i0)
+                    h->z_parts.push_back({(int64_t)i0, (int64_t)i1, item_begin[i0],
+                                          i1 < item_doc.size() ? item_begin[i1] : h->dm.N});
+                i0 = i1;
             }
         }
         h->n_long_docs = (int64_t)long_docs.size();
@@ -843,7 +895,7 @@ int ldagpu_create(int32_t K, int32_t V, int64_t D, const int64_t *doc_offsets, c
         CK(h, h->topic_sum.alloc((size_t)dm.Ks));
         CK(h, h->red.alloc((size_t)N_PARTIALS * 2));
         CK(h, h->red_out.alloc(8));
-        CK(h, h->counter.alloc(1));
+        CK(h, h->counter.alloc(16));
         CK(h, h->bad.alloc(1));
         for (int64_t d = 0; d < D; ++d)
             h->max_doc_len = (int)std::max<int64_t>(h->max_doc_len, doc_offsets[d + 1] - doc_offsets[d]);

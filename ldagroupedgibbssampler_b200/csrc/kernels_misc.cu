@@ -147,26 +147,35 @@ cudaError_t launch_doc_topic_counts(const Dims &dm, const int64_t *doc_off, cons
 
 // 16-bit transport of the topic indicators over PCIe (K <= 65 536): ldagpu_set_z16 / ldagpu_get_z16 /
 // ldagpu_sweep_get_z16 move uint16 and convert on the device; the device copy stays int32
-__global__ void unpack16_kernel(const uint16_t *__restrict__ in, int32_t *__restrict__ out, int64_t n)
+// `head` elements in front of the first 16-byte boundary of the int32 side (the two arrays are offset by the same number
+// of elements, so their vector alignment coincides) and the tail go element by element.
+__global__ void unpack16_kernel(const uint16_t *__restrict__ in, int32_t *__restrict__ out, int64_t n, int head)
 {
-    const int64_t n4 = n / 4, stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n4 = (n - head) / 4, stride = (int64_t)gridDim.x * blockDim.x;
+    const ushort4 *in4 = reinterpret_cast<const ushort4 *>(in + head);
+    int4 *out4 = reinterpret_cast<int4 *>(out + head);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        const ushort4 v = __ldg(reinterpret_cast<const ushort4 *>(in) + i);
-        reinterpret_cast<int4 *>(out)[i] = make_int4(v.x, v.y, v.z, v.w);
+        const ushort4 v = __ldg(in4 + i);
+        out4[i] = make_int4(v.x, v.y, v.z, v.w);
     }
-    if (blockIdx.x == 0)
-        for (int64_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) out[i] = in[i];
+    if (blockIdx.x == 0) {
+        if ((int)threadIdx.x < head) out[threadIdx.x] = in[threadIdx.x];
+        for (int64_t i = head + n4 * 4 + threadIdx.x; i < n; i += blockDim.x) out[i] = in[i];
+    }
 }
-__global__ void pack16_kernel(const int32_t *__restrict__ in, uint16_t *__restrict__ out, int64_t n)
+__global__ void pack16_kernel(const int32_t *__restrict__ in, uint16_t *__restrict__ out, int64_t n, int head)
 {
-    const int64_t n4 = n / 4, stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n4 = (n - head) / 4, stride = (int64_t)gridDim.x * blockDim.x;
+    const int4 *in4 = reinterpret_cast<const int4 *>(in + head);
+    ushort4 *out4 = reinterpret_cast<ushort4 *>(out + head);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        const int4 v = __ldg(reinterpret_cast<const int4 *>(in) + i);
-        reinterpret_cast<ushort4 *>(out)[i] = make_ushort4((unsigned short)v.x, (unsigned short)v.y, (unsigned short)v.z,
-                                                           (unsigned short)v.w);
+        const int4 v = __ldg(in4 + i);
+        out4[i] = make_ushort4((unsigned short)v.x, (unsigned short)v.y, (unsigned short)v.z, (unsigned short)v.w);
     }
-    if (blockIdx.x == 0)
-        for (int64_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) out[i] = (uint16_t)in[i];
+    if (blockIdx.x == 0) {
+        if ((int)threadIdx.x < head) out[threadIdx.x] = (uint16_t)in[threadIdx.x];
+        for (int64_t i = head + n4 * 4 + threadIdx.x; i < n; i += blockDim.x) out[i] = (uint16_t)in[i];
+    }
 }
 static unsigned copy_grid(int64_t n, int sm_count)
 {
@@ -174,16 +183,21 @@ static unsigned copy_grid(int64_t n, int sm_count)
     if (need < grid) grid = need;
     return (unsigned)(grid < 1 ? 1 : grid);
 }
+static int vec_head(const int32_t *p32, int64_t n)
+{
+    const int h = (int)((4 - (reinterpret_cast<uintptr_t>(p32) / sizeof(int32_t)) % 4) % 4);
+    return (int64_t)h < n ? h : (int)n;
+}
 cudaError_t launch_unpack16(const uint16_t *in, int32_t *out, int64_t n, int sm_count, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
-    unpack16_kernel<<<copy_grid(n, sm_count), 256, 0, st>>>(in, out, n);
+    unpack16_kernel<<<copy_grid(n, sm_count), 256, 0, st>>>(in, out, n, vec_head(out, n));
     return cudaGetLastError();
 }
 cudaError_t launch_pack16(const int32_t *in, uint16_t *out, int64_t n, int sm_count, cudaStream_t st)
 {
     if (n <= 0) return cudaSuccess;
-    pack16_kernel<<<copy_grid(n, sm_count), 256, 0, st>>>(in, out, n);
+    pack16_kernel<<<copy_grid(n, sm_count), 256, 0, st>>>(in, out, n, vec_head(in, n));
     return cudaGetLastError();
 }
 

@@ -204,7 +204,10 @@ __device__ __forceinline__ void theta_draw_doc(int *cg, unsigned short *plist, c
     //      (ballot + popc, all lanes) and the list is drained whenever another 32 might not fit
     //      TH_W cells of the lane go through the attempt side by side (gamma_attempt_squeeze_w: independent
     //      dependency chains in one basic block; the values are those of the scalar attempt)
-    constexpr int TH_W = 2;
+#ifndef TH_W_DEF
+#define TH_W_DEF 2
+#endif
+    constexpr int TH_W = TH_W_DEF;
 #pragma unroll 1
     for (int q = 0; q < NT * 4; q += TH_W) {
         int p[TH_W];
@@ -388,19 +391,23 @@ __global__ void __launch_bounds__(z_warps<NT, PCGS>() * 32, z_minb<NT, PCGS>()) 
         }
 
         bool row_in_flight = false;    // the row of this block's first token was requested by the previous block
-        int w = (t0 + lane < t1) ? a.tokens[t0 + lane] : -1;
-        for (int64_t tb0 = t0; tb0 < t1; tb0 += 32) {
-            const int64_t t = tb0 + lane;
-            const bool valid = t < t1;
-            const int nvalid = (int)((t1 - tb0) < 32 ? (t1 - tb0) : 32);
-            const bool more = tb0 + 32 < t1;
-            const int w_next = (t + 32 < t1) ? a.tokens[t + 32] : -1;     // next block's word types, loaded early
-            const int zold = (PCGS && valid) ? a.z[t] : 0;
+        // 32-bit offsets inside the item (an item is at most one document: < 2^31 tokens) keep the loop state small
+        const int ntok = (int)(t1 - t0);
+        const int32_t *const tok = a.tokens + t0;
+        int32_t *const zz = a.z + t0;
+        int w = lane < ntok ? tok[lane] : -1;
+        for (int o = 0; o < ntok; o += 32) {
+            const int idx = o + lane;
+            const bool valid = idx < ntok;
+            const int nvalid = ntok - o < 32 ? ntok - o : 32;
+            const bool more = o + 32 < ntok;
+            const int w_next = (idx + 32 < ntok) ? tok[idx + 32] : -1;     // next block's word types, loaded early
+            const int zold = (PCGS && valid) ? zz[idx] : 0;
             const int wprev = __shfl_up_sync(FULL, w, 1);
             const unsigned heads = __ballot_sync(FULL, valid && (lane == 0 || w != wprev));
             float U = 0.0f;
             if (valid) {
-                unsigned long long gt = (unsigned long long)(a.dm.token_base + t);
+                unsigned long long gt = (unsigned long long)(a.dm.token_base + t0 + idx);
                 uint4 r = philox4x32_10((uint32_t)gt, (uint32_t)(gt >> 32), a.sweep, STREAM_Z << 24, a.rk);
                 U = uniform23(r.x);
             }
@@ -457,7 +464,7 @@ __global__ void __launch_bounds__(z_warps<NT, PCGS>() * 32, z_minb<NT, PCGS>()) 
             }
             row_in_flight = more;
             if (valid) {
-                a.z[t] = znew;
+                zz[idx] = znew;
                 // fused count rebuild (the reference adds its +-1 deltas inside the token loop too,
                 // UncollapsedParallelLDA.java:1505,1542): fire-and-forget reductions
                 if (a.n_wk_out) atomicAdd(&a.n_wk_out[(size_t)w * Ks + pos_of<NT>(znew)], 1);

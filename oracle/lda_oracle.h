@@ -60,7 +60,10 @@ double oracle_c_gamma_f64(double a, uint64_t seed, uint64_t cell, uint32_t sweep
 double oracle_f_gamma(double a, uint64_t seed, uint64_t cell, uint32_t sweep, uint32_t stream,
                       int variant);
 
-/* categorical draw of the contract: a[K] * phirow[K], uniform U */
+/* categorical draw of the contract: a[K] * phirow[K], uniform U.  Two prefix trees, like the kernels:
+ * K <= 1024 lane-contiguous (lane l of 32 owns L = 4*NT consecutive topics, one warp scan of the lane totals),
+ * K > 1024 tile-major (128-topic tiles, distributed butterfly + per-tile scan).  Same selection rule -- first k
+ * with cumsum_k >= U*sum in natural topic order (GGS:96-113, UPL:1507-1526) -- different fp32 rounding. */
 int32_t oracle_draw_topic_contract(const float *a, const float *phirow, int32_t K, float U);
 
 /* GGS theta draw; reference: LDAGroupedGibbsSampler.java:60-72, ParallelDirichlet.java:46-70 */

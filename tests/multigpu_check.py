@@ -18,12 +18,62 @@ import ldagroupedgibbssampler_b200 as L  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 
+def stress(rank, world, local, sweeps):
+    """Exchange-protocol stress in place of racecheck (compute-sanitizer is closed on this pool): an Enron-shaped PCGS
+    slice, `sweeps` single-sweep calls with random per-rank host sleeps between them (every rank its own random stream, so
+    the ranks arrive skewed), stand-alone count rebuilds and Phi redraws mixed in, and the final state must equal the
+    oracle's on the whole corpus bit for bit -- in whichever exchange mode LDAGPU_EXCHANGE selects."""
+    import time
+    K, V, alpha, beta, seed = 400, 28102, 0.125, 0.01, 2019
+    off, tokens = L.synth_corpus(3000, V, 161.0, seed=20190529)
+    cfg = L.LDAConfiguration(scheme="gpu_pcgs", topics=K, alpha=alpha, beta=beta, seed=seed, exec_time=0)
+    s = L.GpuLDASampler(cfg, device=local)
+    box = [L.GpuLDASampler.make_comm_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    s.addInstances(L.InstanceList.from_csr(off, tokens, V), rank=rank, world=world, comm_id=box[0])
+    rng = np.random.default_rng(1000 + rank)
+    for i in range(sweeps):
+        if rng.random() < 0.4:
+            time.sleep(float(rng.uniform(0, 0.004)))
+        s.sample(1)
+        if i % 17 == 5:                       # same call sequence on every rank, different timing
+            s._step("rebuild_counts")
+        if i % 29 == 7:
+            s.getTopicTotals()
+    zs = [None] * world
+    dist.all_gather_object(zs, s.get_z_flat())
+    z = np.concatenate(zs)
+    n_wk, phi = s.getTypeTopicMatrix(), s.getPhi().T.astype(np.float32)
+    mode = s.getExchangeMode()
+    s.close()
+    ok = True
+    if rank == 0:
+        z0 = O.java_next_ints(seed, K, len(tokens))
+        nw0, _ = O.rebuild_counts(tokens, z0, V, K)
+        st = O.sweeps("contract", O.PCGS, off, tokens, z0, V, K, np.full(K, alpha), beta, seed, 1, sweeps,
+                      O.phi_contract(nw0, beta, seed, 0))
+        checks = dict(z=np.array_equal(z, st["z"]), n_wk=np.array_equal(n_wk, st["n_wk"]), phi=np.array_equal(phi, st["phiT"]))
+        print(f"stress: {sweeps} sweeps, world {world}, exchange {mode}:", checks, flush=True)
+        ok = all(checks.values())
+    return ok
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl")
     ok = True
+    if "--stress" in sys.argv:
+        ok = stress(rank, world, local, int(sys.argv[sys.argv.index("--stress") + 1]))
+        t = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        dist.destroy_process_group()
+        if int(t.item()) != 1:
+            sys.exit(1)
+        if rank == 0:
+            print("multigpu stress ok, world =", world)
+        return
     for scheme, osch, K, V in (("gpu_ggs", O.GGS, 100, 900), ("gpu_pcgs", O.PCGS, 400, 1300), ("gpu_ggs", O.GGS, 1000, 2100),
                                ("gpu_spalias", O.SPALIAS, 1500, 700)):
         alpha, beta, seed = 50.0 / K, 0.01, 2019

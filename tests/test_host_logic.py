@@ -211,3 +211,62 @@ def test_synth_corpus_is_shardable_and_deterministic():
     for d in range(0, 600, 97):     # bag of words: sorted inside a document
         seg = a_tok[a_off[d]:a_off[d + 1]]
         assert np.all(np.diff(seg) >= 0)
+
+
+def test_jni_stub_type_checks_against_the_c_abi():
+    """java/jni/ldagpu_jni.c (the binding for JDK 8-21) must keep compiling against include/ldagpu.h: gcc
+    -fsyntax-only with a minimal stand-in for <jni.h> (no JDK in the image), warnings as errors."""
+    import subprocess
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        "-I", os.path.join(ROOT, "tests", "jni_stub"), os.path.join(ROOT, "java", "jni", "ldagpu_jni.c")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_java_shim_binds_only_declared_entry_points():
+    """Every C symbol the Panama shim looks up (fn("ldagpu_...")) is declared in include/ldagpu.h."""
+    src = open(os.path.join(ROOT, "java", "cc", "mallet", "topics", "GpuLDASampler.java")).read()
+    used = set(re.findall(r'fn\("(ldagpu_[a-z0-9_]+)"', src))
+    assert used and used <= set(L.SYMBOLS), used - set(L.SYMBOLS)
+
+
+def test_row_layout_permutation_is_a_bijection_with_contiguous_lane_ownership(tmp_path):
+    """common.cuh tpos / ttopic: for NT = 1, 2, 4, 8 the column of topic k is a bijection on
+    [0, 128*NT), ttopic inverts it, and the float4 that lane l reads from tile j holds the lane's consecutive topics
+    l*L + 4j .. l*L + 4j + 3 (L = 4*NT) -- the ownership the contract's prefix tree (oracle: draw_topic_contract_lanes)
+    assumes.  Compiled with nvcc and run on the host (the functions are __host__ __device__)."""
+    import subprocess
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not os.path.exists(nvcc):
+        pytest.skip("no nvcc")
+    src = tmp_path / "perm.cu"
+    src.write_text(r'''
+#include <cstdio>
+#include <vector>
+#include "common.cuh"
+using namespace ldagpu;
+int main() {
+    for (int nt : {1, 2, 4, 8}) {
+        const int lg = nt == 1 ? 2 : nt == 2 ? 3 : nt == 4 ? 4 : 5, L = 4 * nt, Ks = 128 * nt;
+        std::vector<int> seen(Ks, 0);
+        for (int k = 0; k < Ks; ++k) {
+            const int p = tpos_lg(lg, k);
+            if (p < 0 || p >= Ks || seen[p]++) { std::printf("not a bijection nt=%d k=%d\n", nt, k); return 1; }
+            if (ttopic_lg(lg, p) != k) { std::printf("inverse nt=%d k=%d\n", nt, k); return 1; }
+            const int lane = k / L, m = k % L, j = m / 4, i = m % 4;
+            if (p != 128 * j + 4 * lane + i) { std::printf("ownership nt=%d k=%d\n", nt, k); return 1; }
+        }
+    }
+    for (int k = 0; k < 30000; ++k)   // lg == 2: natural order for any K (K <= 128, K > 1024, sparse schemes)
+        if (tpos_lg(2, k) != k || ttopic_lg(2, k) != k) { std::printf("identity k=%d\n", k); return 1; }
+    std::puts("ok");
+    return 0;
+}
+''')
+    exe = tmp_path / "perm"
+    inc = os.path.join(ROOT, "ldagroupedgibbssampler_b200", "csrc")
+    r = subprocess.run([nvcc, "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-I", inc, str(src), "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout
