@@ -1123,3 +1123,5 @@ void oracle_baseline_sweeps(int scheme, int64_t D, int32_t V, int32_t K, const i
 }
 
 int oracle_max_threads(void) { return omp_get_max_threads(); }
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the checker on rank 0 may take the host back */
+void oracle_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }

@@ -140,6 +140,7 @@ void oracle_baseline_sweeps(int scheme, int64_t D, int32_t V, int32_t K, const i
                             uint64_t seed, int32_t n_sweeps, int32_t n_threads, double *z_seconds,
                             double *phi_seconds);
 int oracle_max_threads(void);
+void oracle_set_num_threads(int n);
 
 /* ---- sparse PCGS z-step ("spalias"), lda_oracle_sparse.c -------------------------------------
  * reference: topics/SpaliasUncollapsedParallelLDA.java:39-60,124-312, util/OptimizedGentleAliasMethod.java:52-107 */

@@ -92,6 +92,7 @@ def lib():
     sig("oracle_baseline_sweeps", None, C.c_int, i64, i32, i32, _i64p, _i32p, _i32p, _f64p, f64,
         u64, i32, i32, C.POINTER(f64), C.POINTER(f64))
     sig("oracle_max_threads", C.c_int)
+    sig("oracle_set_num_threads", None, C.c_int)
     sig("oracle_alias_build_contract", None, i32, i32, _f64p, _f32p, _f32p, _i32p, _f32p)
     sig("oracle_z_spalias_contract", None, i64, _i64p, _i32p, _i32p, i32, _f32p, _f32p, _i32p, _f32p, u64, u32, i64)
     sig("oracle_z_spalias_faithful", None, i64, i32, _i64p, _i32p, _i32p, i32, _f64p, _f64p, u64, u32, i64)
@@ -102,6 +103,10 @@ def lib():
 # --------------------------------------------------------------------------------------------
 # thin numpy-level helpers
 # --------------------------------------------------------------------------------------------
+def set_num_threads(n: int):
+    lib().oracle_set_num_threads(int(n))
+
+
 def philox(ctr, key):
     out = np.zeros(4, np.uint32)
     lib().oracle_philox4x32_10(np.asarray(ctr, np.uint32), np.asarray(key, np.uint32), out)

@@ -23,7 +23,10 @@ def stress(rank, world, local, sweeps):
     slice, `sweeps` single-sweep calls with random per-rank host sleeps between them (every rank its own random stream, so
     the ranks arrive skewed), stand-alone count rebuilds and Phi redraws mixed in, and the final state must equal the
     oracle's on the whole corpus bit for bit -- in whichever exchange mode LDAGPU_EXCHANGE selects."""
+    import faulthandler
     import time
+    if os.environ.get("LDAGPU_STRESS_DUMP_AFTER"):   # where is every rank if the run stalls?
+        faulthandler.dump_traceback_later(float(os.environ["LDAGPU_STRESS_DUMP_AFTER"]), exit=True)
     K, V, alpha, beta, seed = 400, 28102, 0.125, 0.01, 2019
     off, tokens = L.synth_corpus(3000, V, 161.0, seed=20190529)
     cfg = L.LDAConfiguration(scheme="gpu_pcgs", topics=K, alpha=alpha, beta=beta, seed=seed, exec_time=0)
@@ -32,6 +35,7 @@ def stress(rank, world, local, sweeps):
     dist.broadcast_object_list(box, src=0)
     s.addInstances(L.InstanceList.from_csr(off, tokens, V), rank=rank, world=world, comm_id=box[0])
     rng = np.random.default_rng(1000 + rank)
+    t_loop = time.time()
     for i in range(sweeps):
         if rng.random() < 0.4:
             time.sleep(float(rng.uniform(0, 0.004)))
@@ -40,14 +44,17 @@ def stress(rank, world, local, sweeps):
             s._step("rebuild_counts")
         if i % 29 == 7:
             s.getTopicTotals()
+    print(f"[rank {rank}] stress loop done after {time.time() - t_loop:.1f} s", flush=True)
     zs = [None] * world
     dist.all_gather_object(zs, s.get_z_flat())
     z = np.concatenate(zs)
     n_wk, phi = s.getTypeTopicMatrix(), s.getPhi().T.astype(np.float32)
     mode = s.getExchangeMode()
     s.close()
+    faulthandler.cancel_dump_traceback_later()
     ok = True
     if rank == 0:
+        O.set_num_threads(os.cpu_count() or 1)
         z0 = O.java_next_ints(seed, K, len(tokens))
         nw0, _ = O.rebuild_counts(tokens, z0, V, K)
         st = O.sweeps("contract", O.PCGS, off, tokens, z0, V, K, np.full(K, alpha), beta, seed, 1, sweeps,
@@ -64,6 +71,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl")
     ok = True
+    O.set_num_threads(max(1, (os.cpu_count() or 1) // world))   # torchrun exports OMP_NUM_THREADS=1
     if "--stress" in sys.argv:
         ok = stress(rank, world, local, int(sys.argv[sys.argv.index("--stress") + 1]))
         t = torch.tensor([1 if ok else 0], device="cuda")

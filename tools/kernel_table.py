@@ -53,8 +53,11 @@ def main():
 
     def row(name, kernels, ms, alg_bytes, note=""):
         gbs = alg_bytes / (ms / 1e3) / 1e9
+        # SURVEY 8(d) algorithmic bytes over the phase's time: a MODEL figure (for the z-step it charges one Phi^T row per
+        # token and exceeds the HBM peak when rows are shared or cached); the roofline fraction from measured DRAM bytes
+        # is in profiles/z_kernel_traffic.json and in bench.py's `roofline`
         rows.append({"phase": name, "kernels": kernels, "ms": round(ms, 4), "algorithmic_bytes": int(alg_bytes),
-                     "achieved_gbs": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4), "note": note})
+                     "model_gbs": round(gbs, 1), "frac_model": round(gbs / peak, 4), "note": note})
 
     if ggs:
         row("theta draw (GGS)", "theta_kernel", timed(lambda: s._step("sample_theta")), 4 * N + 4 * K * D,
