@@ -34,6 +34,9 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef Z_WARPS_GGS8
 #define Z_WARPS_GGS8 8
 #endif
+#ifndef Z_TH_REG
+#define Z_TH_REG 6   // theta tiles of the 8-tile GGS kernel kept in registers (the rest in shared memory)
+#endif
 // warps per CTA / CTAs per SM.  GGS at 1024 topics keeps theta (32 registers) and the prefixes (32) live;
 // 24 warps per SM leave 80 registers per thread (profiles/README.md, round 2)
 template <int NT, bool PCGS> __host__ __device__ constexpr int z_warps() { return (NT == 8 && !PCGS) ? Z_WARPS_GGS8 : 8; }
@@ -49,17 +52,24 @@ template <int NT> struct RowScan {
 };
 
 // Scores, lane-local prefix, warp scan of the lane totals (contract: DESIGN.md 4.2).
-template <int NT>
-__device__ __forceinline__ void scan_scores(const float4 (&a)[NT], const float4 (&ph)[NT], RowScan<NT> &rs, int lane)
+// The first NREG tiles of the per-document vector come from registers, the others from the lane's float4 in shared
+// memory (a_sm[(j - NREG) * 32 + lane]): at 8 tiles theta (32 registers) and the prefixes (32) do not fit 80
+// registers together, and two LDS.128 per run are cheaper than the eight local-memory reloads the compiler spills to.
+template <int NT, int NREG>
+__device__ __forceinline__ void scan_scores(const float4 (&a)[NREG], const float4 *a_sm, const float4 (&ph)[NT],
+                                            RowScan<NT> &rs, int lane)
 {
     float run = 0.0f;
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
+        float4 aj;
+        if (j < NREG) aj = a[j < NREG ? j : 0];
+        else aj = a_sm[(j - NREG) * 32 + lane];
         // one product starts the lane's chain, every other topic is one fused multiply-add
-        const float p0 = j == 0 ? __fmul_rn(a[j].x, ph[j].x) : __fmaf_rn(a[j].x, ph[j].x, run);
-        const float p1 = __fmaf_rn(a[j].y, ph[j].y, p0);
-        const float p2 = __fmaf_rn(a[j].z, ph[j].z, p1);
-        const float p3 = __fmaf_rn(a[j].w, ph[j].w, p2);
+        const float p0 = j == 0 ? __fmul_rn(aj.x, ph[j].x) : __fmaf_rn(aj.x, ph[j].x, run);
+        const float p1 = __fmaf_rn(aj.y, ph[j].y, p0);
+        const float p2 = __fmaf_rn(aj.z, ph[j].z, p1);
+        const float p3 = __fmaf_rn(aj.w, ph[j].w, p2);
         rs.p[j][0] = p0; rs.p[j][1] = p1; rs.p[j][2] = p2; rs.p[j][3] = p3;
         run = p3;
     }
@@ -87,10 +97,18 @@ __device__ __forceinline__ int draw_topic(const RowScan<NT> &rs, float U, int la
     int jsel = 0;
     float q0 = rs.p[0][0], q1 = rs.p[0][1], q2 = rs.p[0][2];
     if (NT > 1) {
-        // the prefixes never decrease (scores >= 0): the tiles whose last prefix is < r come first
+        // the prefixes never decrease (scores >= 0): the tiles whose last prefix is < r come first, so their number
+        // is a binary search over the NT - 1 tile ends (three dependent compares at 8 tiles instead of seven)
         int jc = 0;
+        if (NT == 8) {
+            jc = rs.p[3][3] < r ? 4 : 0;
+            jc += (jc ? rs.p[5][3] : rs.p[1][3]) < r ? 2 : 0;
+            const float lo = (jc & 2) ? rs.p[2][3] : rs.p[0][3], hi = (jc & 2) ? rs.p[6][3] : rs.p[4][3];
+            jc += ((jc & 4) ? hi : lo) < r ? 1 : 0;
+        } else {
 #pragma unroll
-        for (int j = 0; j + 1 < NT; ++j) jc += (rs.p[j][3] >= r) ? 0 : 1;
+            for (int j = 0; j + 1 < NT; ++j) jc += (rs.p[j][3] >= r) ? 0 : 1;
+        }
         jsel = __shfl_sync(FULL, jc, ls);   // warp-uniform: a real branch picks the tile's registers
 #define LDAGPU_PICK(J)                                                                              \
     case J:                                                                                         \
@@ -299,6 +317,10 @@ __global__ void __launch_bounds__(z_warps<NT, PCGS>() * 32, z_minb<NT, PCGS>()) 
     int *cnt = reinterpret_cast<int *>(wbase + (size_t)ROWF * 4);   // PCGS: n_dk by column
     float *av = reinterpret_cast<float *>(wbase + (size_t)ROWF * 8);   // PCGS: n_dk + alpha by column
     unsigned short *plist = reinterpret_cast<unsigned short *>(wbase + (size_t)ROWF * 4);   // GGS: pending theta cells
+    // GGS at 8 tiles: theta tiles 6 and 7 stay in shared memory -- the 1 KB of the pending list, idle once theta is drawn
+    constexpr int TH_REG = (NT == 8 && !PCGS) ? Z_TH_REG : NT;
+    static_assert((NT - TH_REG) * 32 * 16 <= TH_PLIST * 2, "the theta tiles kept in shared memory must fit the pending list");
+    float4 *th_sm = reinterpret_cast<float4 *>(plist);
     float *cta_f = reinterpret_cast<float *>(smem_raw + Z_WARPS * z_warp_smem<NT, PCGS>());
     float *alpha_s = cta_f;                                         // PCGS: alpha by column
     uint64_t *const bar = reinterpret_cast<uint64_t *>(smem_raw + Z_WARPS * z_warp_smem<NT, PCGS>() +
@@ -341,7 +363,7 @@ __global__ void __launch_bounds__(z_warps<NT, PCGS>() * 32, z_minb<NT, PCGS>()) 
         if (lane == 0) claimed = atomicAdd(a.work_counter, 1ull);
 
         int64_t d, t0, t1;
-        float4 th[NT];
+        float4 th[TH_REG];
         if (PCGS) {
             d = a.item_doc[item];
             t0 = a.doc_off[d];
@@ -378,15 +400,22 @@ __global__ void __launch_bounds__(z_warps<NT, PCGS>() * 32, z_minb<NT, PCGS>()) 
                                    (unsigned long long)(a.dm.doc_base + d) * (unsigned long long)K, a.sweep, a.rk, lane);
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
-                    th[j] = reinterpret_cast<const float4 *>(slot)[j * 32 + lane];
-                    __stcs(reinterpret_cast<float4 *>(trow) + j * 32 + lane, th[j]);
+                    const float4 v = reinterpret_cast<const float4 *>(slot)[j * 32 + lane];
+                    if (j < TH_REG) th[j < TH_REG ? j : 0] = v;
+                    else th_sm[(j - TH_REG) * 32 + lane] = v;   // the pending list is idle from here on
+                    __stcs(reinterpret_cast<float4 *>(trow) + j * 32 + lane, v);
                 }
                 // the slot goes back to the TMA engine: order the generic-proxy accesses above before its writes
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
             } else {
 #pragma unroll
-                for (int j = 0; j < NT; ++j) th[j] = __ldg(reinterpret_cast<const float4 *>(trow) + j * 32 + lane);
+                for (int j = 0; j < NT; ++j) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(trow) + j * 32 + lane);
+                    if (j < TH_REG) th[j < TH_REG ? j : 0] = v;
+                    else th_sm[(j - TH_REG) * 32 + lane] = v;
+                }
+                if (TH_REG < NT) __syncwarp();
             }
         }
 
@@ -430,7 +459,7 @@ __global__ void __launch_bounds__(z_warps<NT, PCGS>() * 32, z_minb<NT, PCGS>()) 
                 else if (more) request(__shfl_sync(FULL, w_next, 0));
 
                 RowScan<NT> rs;
-                if (!PCGS) scan_scores<NT>(th, ph, rs, lane);
+                if (!PCGS) scan_scores<NT, TH_REG>(th, th_sm, ph, rs, lane);
                 for (int tt = b; tt < e; ++tt) {
                     if (PCGS) {
                         // remove the token from the document counts (UncollapsedParallelLDA.java:1494);
@@ -444,7 +473,7 @@ __global__ void __launch_bounds__(z_warps<NT, PCGS>() * 32, z_minb<NT, PCGS>()) 
                         float4 aa[NT];
 #pragma unroll
                         for (int j = 0; j < NT; ++j) aa[j] = reinterpret_cast<const float4 *>(av)[j * 32 + lane];
-                        scan_scores<NT>(aa, ph, rs, lane);
+                        scan_scores<NT, NT>(aa, nullptr, ph, rs, lane);
                     }
                     const float Ut = __shfl_sync(FULL, U, tt);
                     const int k = draw_topic<NT>(rs, Ut, lane, K);
