@@ -390,8 +390,9 @@ def main():
                           "z_dtype": "uint16" if z16 else "int32", "numa_node": numa,
                           "what": "per step: ldagpu_set_z16 from pinned host z (upload pipelined with the widening and the "
                                   "count rebuild), sample(1, z_out=pinned host z) = ldagpu_sweep_get_z16 (z narrowed and read "
-                                  "back while the Phi draw runs), getTopicTotals; host wall clock, max over ranks; bytes are "
-                                  "per rank"}
+                                  "back in document-aligned parts under the z-step of the following parts; small corpora and "
+                                  "the PCGS schemes: under the Phi draw), getTopicTotals; host wall clock, max over ranks; "
+                                  "bytes are per rank"}
         s.close()
         return res, off, tokens
 
