@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- token-topic samples/sec of one Gibbs sweep (BASELINE.json metric) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload pubmed|pubmed8|nips|enron|wiki8] [--scaling strong|weak]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload pubmed|pubmed8|nips|enron|wiki8|wiki8_polya] [--scaling strong|weak]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...      # the CPU port of the reference's sampler, same metric and config
@@ -47,6 +47,9 @@ WORKLOADS = {
     "wiki8": dict(desc="Wikipedia-shaped sparse PCGS K=10000, V=100000, per-GPU shard = 1/8 of the ~4M-doc corpus "
                        "(BASELINE.json configs[4] at 8 GPUs)",
                   D=500000, V=100000, mean_len=250.0, K=10000, scheme="gpu_spalias", alpha=0.005, beta=0.01, scaling="weak"),
+    "wiki8_polya": dict(desc="Wikipedia-shaped K=10000, V=100000, per-GPU shard = 1/8 of the ~4M-doc corpus, sparse z-step with "
+                             "the Poisson Polya-urn Phi draw (the reference's scheme polyaurn: sparse rows of Phi)",
+                        D=500000, V=100000, mean_len=250.0, K=10000, scheme="gpu_polyaurn", alpha=0.005, beta=0.01, scaling="weak"),
 }
 METRIC = "token-topic samples/sec per Gibbs sweep"
 UNIT = "tokens/s"
@@ -164,7 +167,7 @@ def cpu_baseline(wl, off, tokens, budget_tokens, n_total_tokens, threads):
     o, t = off[: d1 + 1].copy(), tokens[: off[d1]].copy()
     K, V = wl["K"], wl["V"]
     z = O.java_next_ints(SEED, K, len(t))
-    if wl["scheme"] == "gpu_spalias":
+    if wl["scheme"] in ("gpu_spalias", "gpu_polyaurn"):
         # the reference's own sparse sampler (SpaliasUncollapsedParallelLDA), restated in double: per sweep
         # alias tables for all V types + Phi draw (both O(K*V)); per token the sparse walk
         alpha = np.full(K, wl["alpha"])
@@ -353,7 +356,7 @@ def main():
             head |= (pos & 31) == 0        # a run ends at the 32-token block of the warp
             res["fetches_per_token"] = float(head.mean())
         mean_nnz = None
-        if wl["scheme"] == "gpu_spalias":
+        if wl["scheme"] in ("gpu_spalias", "gpu_polyaurn"):
             # SURVEY 8(d) sparse z-step: 12 + 8*nnz_d + 16 bytes per token, nnz_d measured on a sample of documents
             zf, dsamp = s.get_z_flat(), min(len(off) - 1, 20000)
             nnz = np.array([len(np.unique(zf[off[d]:off[d + 1]])) for d in range(dsamp)], np.float64)
@@ -453,17 +456,18 @@ def main():
     # ---- the other BASELINE.json configs on one GPU, measured in the same run (N = 1 only) ------------------------
     if world == 1 and not args.no_secondary and not args.docs:
         sec = {}
-        for nm in ("nips", "enron", "wiki8"):
+        for nm in ("nips", "enron", "wiki8", "wiki8_polya"):
             if nm == args.workload:
                 continue
             w2 = dict(WORKLOADS[nm])
             try:
-                r2, _, _ = measure(nm, w2, w2["scaling"], 50 if nm != "wiki8" else 5, 5 if nm != "wiki8" else 2,
-                                   False, False)
+                big = nm.startswith("wiki8")
+                r2, _, _ = measure(nm, w2, w2["scaling"], 5 if big else 50, 2 if big else 5, False, False)
                 sec[nm] = {"config": make_config(nm, w2, w2["scaling"]), "value": r2["value"], "unit": UNIT,
-                           "ms_per_step": r2["ms_per_step"], "steps": 50 if nm != "wiki8" else 5,
+                           "ms_per_step": r2["ms_per_step"], "steps": 5 if big else 50,
                            "tokens_total": r2["n_total"], "z_kernel_ms_per_launch": r2["zk_ms_per_launch"],
-                           "fetches_per_token": r2.get("fetches_per_token"), "mean_nnz_d": r2["mean_nnz"]}
+                           "fetches_per_token": r2.get("fetches_per_token"), "mean_nnz_d": r2["mean_nnz"],
+                           "timers_ms_since_create": r2["timers"]}
             except Exception as e:   # a side measurement must not take the headline down with it
                 sec[nm] = {"error": str(e)[:200]}
         out["secondary"] = sec
