@@ -35,7 +35,7 @@ constexpr unsigned FULL = 0xffffffffu;
 #define Z_WARPS_GGS8 8
 #endif
 #ifndef Z_TH_REG
-#define Z_TH_REG 6   // theta tiles of the 8-tile GGS kernel kept in registers (the rest in shared memory)
+#define Z_TH_REG 3   // theta tiles of the 8-tile GGS kernel kept in registers (the rest in shared memory; measured 1..8, profiles/README.md)
 #endif
 // warps per CTA / CTAs per SM.  GGS at 1024 topics keeps theta (32 registers) and the prefixes (32) live;
 // 24 warps per SM leave 80 registers per thread (profiles/README.md, round 2)
@@ -295,9 +295,14 @@ __device__ __forceinline__ void theta_draw_doc(int *cg, unsigned short *plist, c
 }
 
 // shared-memory footprint, in bytes
+template <int NT, bool PCGS> __host__ __device__ constexpr int z_th_reg() { return (NT == 8 && !PCGS) ? Z_TH_REG : NT; }
 template <int NT, bool PCGS> __host__ __device__ constexpr size_t z_warp_smem()
 {
-    return (size_t)NT * TILE * 4 + (PCGS ? (size_t)NT * TILE * 8 : (size_t)TH_PLIST * 2);
+    // GGS: row slot + one auxiliary area that is the pending list during the theta draw and the home of the theta tiles
+    // that do not stay in registers afterwards
+    constexpr size_t aux = (size_t)(NT - z_th_reg<NT, PCGS>()) * 32 * 16 > (size_t)TH_PLIST * 2
+                               ? (size_t)(NT - z_th_reg<NT, PCGS>()) * 32 * 16 : (size_t)TH_PLIST * 2;
+    return (size_t)NT * TILE * 4 + (PCGS ? (size_t)NT * TILE * 8 : aux);
 }
 template <int NT, bool PCGS> __host__ __device__ constexpr size_t z_cta_smem()
 {
@@ -317,9 +322,8 @@ __global__ void __launch_bounds__(z_warps<NT, PCGS>() * 32, z_minb<NT, PCGS>()) 
     int *cnt = reinterpret_cast<int *>(wbase + (size_t)ROWF * 4);   // PCGS: n_dk by column
     float *av = reinterpret_cast<float *>(wbase + (size_t)ROWF * 8);   // PCGS: n_dk + alpha by column
     unsigned short *plist = reinterpret_cast<unsigned short *>(wbase + (size_t)ROWF * 4);   // GGS: pending theta cells
-    // GGS at 8 tiles: theta tiles 6 and 7 stay in shared memory -- the 1 KB of the pending list, idle once theta is drawn
-    constexpr int TH_REG = (NT == 8 && !PCGS) ? Z_TH_REG : NT;
-    static_assert((NT - TH_REG) * 32 * 16 <= TH_PLIST * 2, "the theta tiles kept in shared memory must fit the pending list");
+    // GGS at 8 tiles: the theta tiles beyond TH_REG stay in shared memory -- the area of the pending list, idle once theta is drawn
+    constexpr int TH_REG = z_th_reg<NT, PCGS>();
     float4 *th_sm = reinterpret_cast<float4 *>(plist);
     float *cta_f = reinterpret_cast<float *>(smem_raw + Z_WARPS * z_warp_smem<NT, PCGS>());
     float *alpha_s = cta_f;                                         // PCGS: alpha by column
