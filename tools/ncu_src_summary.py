@@ -13,6 +13,9 @@ def main():
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
     hdr = next(r for r in rows if "Instructions Executed" in r)
     ia, isrc, ith, ismp = (hdr.index(x) for x in ("Instructions Executed", "Source", "Avg. Threads Executed", "# Samples"))
+    first = rows.index(hdr)
+    later = [i for i in range(first + 1, len(rows)) if rows[i] == hdr]      # one table per launch: keep the first
+    rows = rows[first:later[0]] if later else rows[first:]
     data = [r for r in rows if len(r) == len(hdr) and r[ia].isdigit()]
     tot = sum(int(r[ia]) for r in data)
     stot = sum(int(r[ismp]) for r in data)
