@@ -165,6 +165,8 @@ struct __align__(8) AliasSlot {
     int32_t alias;
 };
 int64_t alias_scratch_threads(const Dims &dm, int sm_count);
+size_t alias_stack_ints(const Dims &dm, int sm_count);     // ints of the stack scratch (topics + the count pairs)
+size_t alias_value_doubles(const Dims &dm, int sm_count);  // doubles of the value scratch
 cudaError_t launch_alias_build(const Dims &dm, const float *alpha, const float *phiT, AliasSlot *table,
                                float *type_norm, double *bs_scratch, int32_t *stack_scratch,
                                const int32_t *active, int32_t n_active, int sm_count, cudaStream_t st);

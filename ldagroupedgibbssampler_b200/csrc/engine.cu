@@ -289,7 +289,7 @@ int step_alias(ldagpu_handle h)
     CK(h, launch_alias_build(h->dm, h->alpha_f.p, h->phiT.p, h->alias_table.p, h->type_norm.p,
                              h->alias_bs.p, h->alias_stack.p, h->active_types.p, h->n_active_types, h->sm_count,
                              h->stream));
-    h->last_launches += 1;
+    h->last_launches += 2;   // classify + pair (one round unless the vocabulary exceeds the scratch slots)
     return 0;
 }
 
@@ -900,11 +900,10 @@ int ldagpu_create(int32_t K, int32_t V, int64_t D, const int64_t *doc_offsets, c
         for (int64_t d = 0; d < D; ++d)
             h->max_doc_len = (int)std::max<int64_t>(h->max_doc_len, doc_offsets[d + 1] - doc_offsets[d]);
         if (scheme == LDAGPU_SCHEME_SPALIAS) {
-            const size_t T = (size_t)alias_scratch_threads(dm, h->sm_count);
             CK(h, h->alias_table.alloc((size_t)dm.Vp * dm.Ks));
             CK(h, h->type_norm.alloc((size_t)dm.Vp));
-            CK(h, h->alias_bs.alloc(T * (size_t)K));
-            CK(h, h->alias_stack.alloc(T * (size_t)K));
+            CK(h, h->alias_bs.alloc(alias_value_doubles(dm, h->sm_count)));
+            CK(h, h->alias_stack.alloc(alias_stack_ints(dm, h->sm_count)));
             CK(h, h->sparse_lists.alloc(spalias_list_bytes(dm, h->max_doc_len, h->sm_count) / sizeof(int32_t)));
             // only the types that occur in this rank's tokens are ever looked up
             std::vector<char> seen((size_t)V, 0);

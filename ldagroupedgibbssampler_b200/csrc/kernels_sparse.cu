@@ -19,107 +19,174 @@ constexpr unsigned FULL = 0xffffffffu;
 
 // ---------------------------------------------------------------------------------------
 // Alias tables.  The reference's stack algorithm is order dependent, so the pairing loop stays
-// sequential per word type; types are independent.  A warp takes 32 types at a time:
-//   phase A (cooperative, coalesced): for each of the 32 types the lanes stream the Phi^T row, form the
+// sequential per word type; types are independent.  Two kernels per round of T types (T = scratch slots):
+//   alias_classify_kernel (one WARP per type, coalesced): the lanes stream the Phi^T row, form the
 //            normaliser (lane-strided fp64 partial sums + xor butterfly), classify every topic as "low"
-//            (b < 0) or "high" and compact the indices, in topic order, into the type's two stacks
+//            (b < 0) or "high" and compact (topic, b) pairs, in topic order, into the type's two stacks
 //            (ballot + popc prefix) -- the same stacks the sequential classification would build;
-//   phase B (one lane per type): the sequential pairing loop on the type's private scratch
-//            (b[K] fp64, one int stack[K]: "low" from the front, "high" from the back; both are popped
-//            in decreasing order, so the loop walks its own 12 K bytes with sector reuse).
+//   alias_pair_kernel (one LANE per type): the sequential pairing loop on the type's private scratch
+//            (si[K] topics + sb[K] fp64 values in STACK order: "low" from the front, "high" from the back).
+//            Both stacks are consumed top first and nothing is ever pushed back on them (a high that turns low is
+//            the next one popped: it stays in registers), so each is a sequential stream: a lane keeps the next
+//            ALIAS_Q entries of either stack in registers and the warp tops all of them up together whenever one
+//            lane runs dry -- one memory round trip per ALIAS_Q steps instead of two dependent ones per step.
+//            (A deeper prefetch through per-lane rings in shared memory filled by cp.async removed the remaining
+//            load stalls but cost as many extra instructions as it saved cycles: 9.9 ms against 9.05.)
+// Round 1 ran both phases in one kernel, a warp classifying its 32 types one after the other: with ~45 000 active
+// types that is 9.5 warps per SM in long latency-bound loops (ncu: 12 long-scoreboard stalls per issue, 14 % issue
+// utilisation, 20.4 ms at K = 10 000).
 // Only the types that occur in this rank's tokens get a table (no token ever reads the others).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-alias_build_kernel(Dims dm, const float *__restrict__ alpha, const float *__restrict__ phiT,
-                   AliasSlot *__restrict__ table, float *__restrict__ type_norm,
-                   double *__restrict__ bs_all, int32_t *__restrict__ stack_all,
-                   const int32_t *__restrict__ active, int32_t n_active)
+#ifndef ALIAS_Q
+#define ALIAS_Q 4   // stack entries a lane of the pairing kernel holds ahead in registers (measured 2, 4, 8: 9.5, 9.05, 9.3 ms)
+#endif
+#ifndef ALIAS_TPS
+#define ALIAS_TPS 1024   // scratch slots per SM: one round covers 151 552 types
+#endif
+constexpr int ALIAS_CW = 8;   // warps per CTA of the classify kernel
+
+__global__ void __launch_bounds__(ALIAS_CW * 32)
+alias_classify_kernel(Dims dm, const float *__restrict__ alpha, const float *__restrict__ phiT,
+                      AliasSlot *__restrict__ table, float *__restrict__ type_norm,
+                      double *__restrict__ sb_all, int32_t *__restrict__ si_all, int2 *__restrict__ counts,
+                      const int32_t *__restrict__ active, int32_t n)
 {
     const int lane = threadIdx.x & 31;
-    const int64_t T = (int64_t)gridDim.x * blockDim.x;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t warp_first = tid - lane;          // scratch slot of lane 0 of this warp
     const int K = dm.K;
     const double k1 = 1.0 / (double)K;
     const unsigned lt_mask = (1u << lane) - 1u;
-    for (int64_t base = warp_first; base < n_active; base += T) {
-        int mylow = 0, myhigh = 0;
-        // ---- phase A
-        for (int j = 0; j < 32; ++j) {
-            if (base + j >= n_active) break;
-            const int64_t w = active[base + j];
-            const float *ph = phiT + (size_t)w * dm.Ks;
-            AliasSlot *tw = table + (size_t)w * dm.Ks;
-            double *bs = bs_all + (size_t)(warp_first + j) * K;
-            int32_t *stack = stack_all + (size_t)(warp_first + j) * K;
-            double acc = 0.0;
-            for (int k = lane; k < K; k += 32) acc = __dadd_rn(acc, (double)__fmul_rn(alpha[k], ph[k]));
+    const int nwarps = gridDim.x * ALIAS_CW;
+    for (int slot = blockIdx.x * ALIAS_CW + (threadIdx.x >> 5); slot < n; slot += nwarps) {
+        const int64_t w = active[slot];
+        const float *ph = phiT + (size_t)w * dm.Ks;
+        AliasSlot *tw = table + (size_t)w * dm.Ks;
+        double *sb = sb_all + (size_t)slot * K;
+        int32_t *si = si_all + (size_t)slot * K;
+        // normaliser: the lane's terms are added in topic order; four loads are in flight per step
+        double acc = 0.0;
+        int k = lane;
+        for (; k + 96 < K; k += 128) {
+            const float a0 = alpha[k], a1 = alpha[k + 32], a2 = alpha[k + 64], a3 = alpha[k + 96];
+            const float p0 = ph[k], p1 = ph[k + 32], p2 = ph[k + 64], p3 = ph[k + 96];
+            acc = __dadd_rn(acc, (double)__fmul_rn(a0, p0));
+            acc = __dadd_rn(acc, (double)__fmul_rn(a1, p1));
+            acc = __dadd_rn(acc, (double)__fmul_rn(a2, p2));
+            acc = __dadd_rn(acc, (double)__fmul_rn(a3, p3));
+        }
+        for (; k < K; k += 32) acc = __dadd_rn(acc, (double)__fmul_rn(alpha[k], ph[k]));
 #pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(FULL, acc, off));
-            const double norm = acc;
-            if (lane == 0) type_norm[w] = __double2float_rn(norm);
-            int low = 0, high = 0;
-            for (int c0 = 0; c0 < K; c0 += 32) {
-                const int i = c0 + lane;
+        for (int off = 16; off >= 1; off >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(FULL, acc, off));
+        const double norm = acc;
+        if (lane == 0) type_norm[w] = __double2float_rn(norm);
+        int low = 0, high = 0;
+        for (int c0 = 0; c0 < K; c0 += 128) {
+            float av[4], pv[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int i = c0 + 32 * r + lane;
+                av[r] = i < K ? alpha[i] : 0.0f;
+                pv[r] = i < K ? ph[i] : 0.0f;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int i = c0 + 32 * r + lane;
                 const bool valid = i < K;
-                double b = 0.0;
-                if (valid) {
-                    // a type whose Phi column is all zero (possible with the Polya-urn Phi draw) has no prior part:
-                    // its table is never consulted (tn = 0), keep the arithmetic finite
-                    b = norm > 0.0 ? __dsub_rn(__ddiv_rn((double)__fmul_rn(alpha[i], ph[i]), norm), k1) : 0.0;
-                    bs[i] = b;
-                    tw[i] = AliasSlot{0.0f, i};
-                }
+                // a type whose Phi column is all zero (possible with the Polya-urn Phi draw) has no prior part:
+                // its table is never consulted (tn = 0), keep the arithmetic finite
+                const double b = (valid && norm > 0.0)
+                                     ? __dsub_rn(__ddiv_rn((double)__fmul_rn(av[r], pv[r]), norm), k1) : 0.0;
+                if (valid) tw[i] = AliasSlot{0.0f, i};
                 const bool is_low = valid && b < 0.0;
                 const unsigned lm = __ballot_sync(FULL, is_low), hm = __ballot_sync(FULL, valid && !is_low);
-                if (is_low) stack[low + __popc(lm & lt_mask)] = i;
-                else if (valid) stack[K - 1 - (high + __popc(hm & lt_mask))] = i;
+                const int pos = is_low ? low + __popc(lm & lt_mask) : K - 1 - (high + __popc(hm & lt_mask));
+                if (valid) { si[pos] = i; sb[pos] = b; }
                 low += __popc(lm);
                 high += __popc(hm);
             }
-            if (lane == j) { mylow = low; myhigh = high; }
         }
-        __syncwarp();
-        // ---- phase B
-        if (base + lane < n_active) {
-            const int64_t w = active[base + lane];
-            AliasSlot *tw = table + (size_t)w * dm.Ks;
-            double *bs = bs_all + (size_t)tid * K;
-            int32_t *stack = stack_all + (size_t)tid * K;
-            // low stack: stack[0..low), high stack: stack[K-high..K) (top = K-high).  The reference loop
-            //   while (low>0 && high>0) { l = pop low; h = top high; b[h] += b[l]; b[l] = 0;
-            //                             if (b[h] <= 0) pop high; if (b[h] < 0) push h on low; a[l] = h; ps[l] = 1 + K c }
-            // with the two values it keeps re-reading held in registers: the residual of the current top
-            // high, and a high that just turned low (it is pushed on top of the low stack, so it is the
-            // next one popped).  b[] is then read once per topic and never written back.
-            int low = mylow, high = myhigh, h = 0, pl = 0;
-            double d = 0.0, pc = 0.0;
-            bool have_h = false, pending = false;
-            while ((pending || low > 0) && high > 0) {
-                int l;
-                double c;
-                if (pending) { l = pl; c = pc; pending = false; }
-                else { l = stack[--low]; c = bs[l]; }
-                if (!have_h) { h = stack[K - high]; d = bs[h]; have_h = true; }
-                const double nb = __dadd_rn(c, d);
-                d = nb;
-                if (nb <= 0.0) { high--; have_h = false; }
-                if (nb < 0.0) { pending = true; pl = h; pc = nb; }
-                tw[l] = AliasSlot{__double2float_rn(__dadd_rn(1.0, __dmul_rn((double)K, c))), h};
+        if (lane == 0) counts[slot] = make_int2(low, high);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+alias_pair_kernel(Dims dm, AliasSlot *__restrict__ table, const double *__restrict__ sb_all,
+                  const int32_t *__restrict__ si_all, const int2 *__restrict__ counts,
+                  const int32_t *__restrict__ active, int32_t n)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const int K = dm.K;
+    const bool mine = slot < n;
+    AliasSlot *tw = table + (size_t)(mine ? active[slot] : 0) * dm.Ks;
+    const double *sb = sb_all + (size_t)(mine ? slot : 0) * K;
+    const int32_t *si = si_all + (size_t)(mine ? slot : 0) * K;
+    const int2 cn = mine ? counts[slot] : make_int2(0, 0);
+    // low stack: positions [0, low), top = low - 1; high stack: [K - high, K), top = K - high.  The reference loop
+    //   while (low>0 && high>0) { l = pop low; h = top high; b[h] += b[l]; b[l] = 0;
+    //                             if (b[h] <= 0) pop high; if (b[h] < 0) push h on low; a[l] = h; ps[l] = 1 + K c }
+    // with the two values it keeps re-reading held in registers: the residual of the current top
+    // high, and a high that just turned low (it is pushed on top of the low stack, so it is the
+    // next one popped).  Every stack entry is then read once, in stack order.
+    int low = cn.x, high = cn.y, h = 0, pl = 0;
+    int lnext = low - 1, hnext = K - high;      // next positions to fetch (top first); -1 / K: stack exhausted
+    int lq_n = 0, hq_n = 0, lq_i[ALIAS_Q], hq_i[ALIAS_Q];
+    double lq_b[ALIAS_Q], hq_b[ALIAS_Q];
+#pragma unroll
+    for (int r = 0; r < ALIAS_Q; ++r) { lq_i[r] = hq_i[r] = 0; lq_b[r] = hq_b[r] = 0.0; }
+    double d = 0.0, pc = 0.0;
+    bool have_h = false, pending = false;
+    bool act = low > 0 && high > 0;
+    while (__any_sync(FULL, act)) {
+        // every lane tops its queues up whenever one lane runs dry: the loads of a top-up are independent, so the warp
+        // pays one memory round trip per ALIAS_Q steps
+        const bool dry = act && ((!pending && lq_n == 0) || (!have_h && hq_n == 0));
+        if (__any_sync(FULL, dry)) {
+#pragma unroll
+            for (int r = 0; r < ALIAS_Q; ++r) {
+                if (r == lq_n && lnext >= 0) { lq_i[r] = si[lnext]; lq_b[r] = sb[lnext]; --lnext; ++lq_n; }
+                if (r == hq_n && hnext < K) { hq_i[r] = si[hnext]; hq_b[r] = sb[hnext]; ++hnext; ++hq_n; }
             }
         }
-        __syncwarp();
+        if (act) {
+            int l;
+            double c;
+            if (pending) { l = pl; c = pc; pending = false; }
+            else {
+                l = lq_i[0]; c = lq_b[0];
+#pragma unroll
+                for (int r = 0; r + 1 < ALIAS_Q; ++r) { lq_i[r] = lq_i[r + 1]; lq_b[r] = lq_b[r + 1]; }
+                --lq_n; --low;
+            }
+            if (!have_h) {
+                h = hq_i[0]; d = hq_b[0];
+#pragma unroll
+                for (int r = 0; r + 1 < ALIAS_Q; ++r) { hq_i[r] = hq_i[r + 1]; hq_b[r] = hq_b[r + 1]; }
+                --hq_n; have_h = true;
+            }
+            const double nb = __dadd_rn(c, d);
+            d = nb;
+            if (nb <= 0.0) { high--; have_h = false; }
+            if (nb < 0.0) { pending = true; pl = h; pc = nb; }
+            tw[l] = AliasSlot{__double2float_rn(__dadd_rn(1.0, __dmul_rn((double)K, c))), h};
+            act = (pending || low > 0) && high > 0;
+        }
     }
 }
 
 int64_t alias_scratch_threads(const Dims &dm, int sm_count)
 {
-#ifndef ALIAS_TPS
-#define ALIAS_TPS 512
-#endif
     int64_t t = (int64_t)sm_count * ALIAS_TPS;
     int64_t need = ((int64_t)dm.V + 127) / 128 * 128;
     return need < t ? need : t;
+}
+
+// scratch: sb[T][K] doubles; si[T][K] ints followed by the T (low, high) count pairs -- T = alias_scratch_threads()
+size_t alias_value_doubles(const Dims &dm, int sm_count)
+{
+    return (size_t)alias_scratch_threads(dm, sm_count) * (size_t)dm.K;
+}
+size_t alias_stack_ints(const Dims &dm, int sm_count)
+{
+    return alias_value_doubles(dm, sm_count) + 2 * (size_t)alias_scratch_threads(dm, sm_count);
 }
 
 cudaError_t launch_alias_build(const Dims &dm, const float *alpha, const float *phiT, AliasSlot *table,
@@ -128,12 +195,22 @@ cudaError_t launch_alias_build(const Dims &dm, const float *alpha, const float *
 {
     if (n_active == 0) return cudaSuccess;
     const int64_t T = alias_scratch_threads(dm, sm_count);
-    // balanced rounds: when the types do not fit one wave of T threads, split them evenly over the rounds
+    int2 *counts = reinterpret_cast<int2 *>(stack_scratch + (size_t)T * dm.K);   // 8-byte aligned: T is a multiple of 128
+    int per_sm = 1;
+    cudaError_t e = kernel_config(reinterpret_cast<const void *>(alias_classify_kernel), ALIAS_CW * 32, 0, &per_sm);
+    if (e != cudaSuccess) return e;
+    // rounds of up to T types; when they do not fit one round, split them evenly
     const int64_t rounds = ((int64_t)n_active + T - 1) / T;
-    int64_t blocks = (((int64_t)n_active + rounds - 1) / rounds + 127) / 128;
-    if (blocks > T / 128) blocks = T / 128;
-    alias_build_kernel<<<(unsigned)blocks, 128, 0, st>>>(dm, alpha, phiT, table, type_norm, bs_scratch,
-                                                       stack_scratch, active, n_active);
+    const int64_t per_round = ((int64_t)n_active + rounds - 1) / rounds;
+    for (int64_t first = 0; first < n_active; first += per_round) {
+        const int32_t n = (int32_t)(n_active - first < per_round ? n_active - first : per_round);
+        int64_t cgrid = ((int64_t)n + ALIAS_CW - 1) / ALIAS_CW;
+        if (cgrid > (int64_t)sm_count * per_sm) cgrid = (int64_t)sm_count * per_sm;
+        alias_classify_kernel<<<(unsigned)cgrid, ALIAS_CW * 32, 0, st>>>(dm, alpha, phiT, table, type_norm, bs_scratch,
+                                                                        stack_scratch, counts, active + first, n);
+        alias_pair_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(dm, table, bs_scratch, stack_scratch, counts,
+                                                                      active + first, n);
+    }
     return cudaGetLastError();
 }
 
