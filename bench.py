@@ -279,7 +279,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def measure(name, wl, scaling, steps, warmup, with_e2e, with_clocks):
+    def measure(name, wl, scaling, steps, warmup, with_e2e, with_clocks, with_props=True):
         """One workload on this process group: device-resident sweeps, then the end-to-end loop."""
         if scaling == "strong":
             d0, d1 = wl["D"] * rank // world, wl["D"] * (rank + 1) // world      # this rank's documents of the fixed corpus
@@ -396,6 +396,38 @@ def main():
                                   "back in document-aligned parts under the z-step of the following parts; small corpora and "
                                   "the PCGS schemes: under the Phi draw), getTopicTotals; host wall clock, max over ranks; "
                                   "bytes are per rank"}
+        # ---- size-independent properties of the sampler state at the workload's full size (untimed) ----------------
+        if with_props:
+            K, V = wl["K"], wl["V"]
+            zf = s.get_z_flat()
+            n_k = np.asarray(s.getTopicTotals(), np.int64)
+            hist = np.bincount(zf, minlength=K).astype(np.int64)
+            if world > 1:
+                ht = torch.from_numpy(hist).cuda()
+                dist.all_reduce(ht)
+                hist = ht.cpu().numpy()
+            props = {"tokens": int(n_total),
+                     "z_in_range": bool(n_local == 0 or (int(zf.min()) >= 0 and int(zf.max()) < K)),
+                     "n_k_is_histogram_of_z": bool(np.array_equal(n_k, hist)),
+                     "sum_n_k_is_N": int(n_k.sum()) == int(n_total)}
+            if world == 1 and K * V <= 200_000_000:
+                n_wk = s.getTypeTopicMatrix()
+                props["n_wk_column_sums_are_n_k"] = bool(np.array_equal(n_wk.sum(axis=0, dtype=np.int64), n_k))
+                props["n_wk_row_sums_are_type_counts"] = bool(np.array_equal(
+                    n_wk.sum(axis=1, dtype=np.int64), np.bincount(tokens, minlength=V).astype(np.int64)))
+                s._step("rebuild_counts")                      # idempotence: the rebuild from the same z changes nothing
+                props["count_rebuild_idempotent"] = bool(np.array_equal(s.getTypeTopicMatrix(), n_wk))
+                del n_wk
+                phi = s.getPhi()
+                props["phi_rows_sum_to_1"] = bool(np.all(np.abs(phi.sum(axis=1) - 1.0) < 1e-4))
+                if wl["scheme"] != "gpu_polyaurn":             # the urn keeps exact zeros
+                    props["phi_positive"] = bool(phi.min() > 0.0)
+                del phi
+            del zf
+            bad = [k for k, v in props.items() if v is False]
+            if bad:
+                raise RuntimeError(f"{name}: state properties violated at full size: {bad}")
+            res["properties"] = props
         s.close()
         return res, off, tokens
 
@@ -447,7 +479,9 @@ def main():
            "run": {"exchange": res["exchange"], "tokens_total": res["n_total"], "tokens_per_gpu": res["sizes"],
                    "corpus_gen_s": round(res["gen_s"], 1), "wall_ms_per_step": res["wall_ms_per_step"]},
            "clocks": res["clocks"], "e2e": res["e2e"], "gpu_launches": res["launches"], "roofline": roofline,
-           "timers_ms": res["timers"]}
+           "timers_ms": res["timers"],
+           "properties": dict(res["properties"], what="checked after the timed loops on the state of the whole workload, "
+                                                       "untimed; a violated property aborts the run")}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"], _ = cpu_baseline(wl, off, tokens, args.cpu_sample_tokens, res["n_total"], os.cpu_count() or 1)
@@ -467,7 +501,7 @@ def main():
                            "ms_per_step": r2["ms_per_step"], "steps": 5 if big else 50,
                            "tokens_total": r2["n_total"], "z_kernel_ms_per_launch": r2["zk_ms_per_launch"],
                            "fetches_per_token": r2.get("fetches_per_token"), "mean_nnz_d": r2["mean_nnz"],
-                           "timers_ms_since_create": r2["timers"]}
+                           "timers_ms_since_create": r2["timers"], "properties": r2.get("properties")}
             except Exception as e:   # a side measurement must not take the headline down with it
                 sec[nm] = {"error": str(e)[:200]}
         out["secondary"] = sec
