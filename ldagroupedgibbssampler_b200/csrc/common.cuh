@@ -165,11 +165,11 @@ struct __align__(8) AliasSlot {
     int32_t alias;
 };
 int64_t alias_scratch_threads(const Dims &dm, int sm_count);
-size_t alias_stack_ints(const Dims &dm, int sm_count);     // ints of the stack scratch (topics + the count pairs)
-size_t alias_value_doubles(const Dims &dm, int sm_count);  // doubles of the value scratch
+size_t alias_stack_ints(const Dims &dm, int64_t T);     // ints of the stack scratch for T slots (topics + the count pairs)
+size_t alias_value_doubles(const Dims &dm, int64_t T);  // doubles of the value scratch for T slots
 cudaError_t launch_alias_build(const Dims &dm, const float *alpha, const float *phiT, AliasSlot *table,
                                float *type_norm, double *bs_scratch, int32_t *stack_scratch,
-                               const int32_t *active, int32_t n_active, int sm_count, cudaStream_t st);
+                               const int32_t *active, int32_t n_active, int64_t slots, int sm_count, cudaStream_t st);
 size_t spalias_list_bytes(const Dims &dm, int max_doc_len, int sm_count);
 cudaError_t launch_z_spalias(const ZArgs &z, const AliasSlot *table, const float *type_norm,
                              int *lists, int max_doc_len, int sm_count, cudaStream_t st);

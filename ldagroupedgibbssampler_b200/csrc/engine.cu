@@ -140,6 +140,7 @@ struct ldagpu_handle_s {
     DevBuf<int32_t> alias_stack, active_types, sparse_lists;
     int32_t n_active_types = 0;
     DevBuf<double> alias_bs;
+    int64_t alias_slots = 0;   // types per round of the alias-table kernels (scratch slots)
     int max_doc_len = 0;
     DevBuf<double> alpha_d, lgs_alpha, partial, seg, topic_sum, phi_mean, red, red_out, scratch_f64;
     DevBuf<unsigned long long> counter;
@@ -287,9 +288,10 @@ int step_alias(ldagpu_handle h)
 {
     if (h->scheme != LDAGPU_SCHEME_SPALIAS) return 0;
     CK(h, launch_alias_build(h->dm, h->alpha_f.p, h->phiT.p, h->alias_table.p, h->type_norm.p,
-                             h->alias_bs.p, h->alias_stack.p, h->active_types.p, h->n_active_types, h->sm_count,
-                             h->stream));
-    h->last_launches += 2;   // classify + pair (one round unless the vocabulary exceeds the scratch slots)
+                             h->alias_bs.p, h->alias_stack.p, h->active_types.p, h->n_active_types, h->alias_slots,
+                             h->sm_count, h->stream));
+    // classify + pair per round (one round unless the active vocabulary exceeds the scratch slots)
+    h->last_launches += 2 * (int)((h->n_active_types + h->alias_slots - 1) / std::max<int64_t>(h->alias_slots, 1));
     return 0;
 }
 
@@ -902,8 +904,9 @@ int ldagpu_create(int32_t K, int32_t V, int64_t D, const int64_t *doc_offsets, c
         if (scheme == LDAGPU_SCHEME_SPALIAS) {
             CK(h, h->alias_table.alloc((size_t)dm.Vp * dm.Ks));
             CK(h, h->type_norm.alloc((size_t)dm.Vp));
-            CK(h, h->alias_bs.alloc(alias_value_doubles(dm, h->sm_count)));
-            CK(h, h->alias_stack.alloc(alias_stack_ints(dm, h->sm_count)));
+            h->alias_slots = alias_scratch_threads(dm, h->sm_count);
+            CK(h, h->alias_bs.alloc(alias_value_doubles(dm, h->alias_slots)));
+            CK(h, h->alias_stack.alloc(alias_stack_ints(dm, h->alias_slots)));
             CK(h, h->sparse_lists.alloc(spalias_list_bytes(dm, h->max_doc_len, h->sm_count) / sizeof(int32_t)));
             // only the types that occur in this rank's tokens are ever looked up
             std::vector<char> seen((size_t)V, 0);

@@ -10,6 +10,8 @@
 // Cost per token is O(nnz_d) gathered Phi entries instead of the dense step's K: 12 + ~32 nnz_d bytes
 // (a 4-byte gather costs a 32-byte sector) against 4 K.  Arithmetic contract: DESIGN.md 4.6; the CPU
 // oracle (oracle/lda_oracle_sparse.c) reproduces tables and z bit for bit.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "contract_math.cuh"
 
@@ -172,29 +174,29 @@ alias_pair_kernel(Dims dm, AliasSlot *__restrict__ table, const double *__restri
     }
 }
 
+// scratch slots (types per round of the two kernels): all of the vocabulary when it fits sm_count * ALIAS_TPS slots.
+// LDAGPU_ALIAS_SLOTS caps it -- 12 K bytes of scratch per slot (1.2 GB per 10 000 slots at K = 10 000); the tables do
+// not depend on it, only the number of rounds.
 int64_t alias_scratch_threads(const Dims &dm, int sm_count)
 {
     int64_t t = (int64_t)sm_count * ALIAS_TPS;
+    if (const char *e = getenv("LDAGPU_ALIAS_SLOTS")) {
+        const long long v = atoll(e);
+        if (v > 0 && v < t) t = (v + 127) / 128 * 128;
+    }
     int64_t need = ((int64_t)dm.V + 127) / 128 * 128;
     return need < t ? need : t;
 }
 
-// scratch: sb[T][K] doubles; si[T][K] ints followed by the T (low, high) count pairs -- T = alias_scratch_threads()
-size_t alias_value_doubles(const Dims &dm, int sm_count)
-{
-    return (size_t)alias_scratch_threads(dm, sm_count) * (size_t)dm.K;
-}
-size_t alias_stack_ints(const Dims &dm, int sm_count)
-{
-    return alias_value_doubles(dm, sm_count) + 2 * (size_t)alias_scratch_threads(dm, sm_count);
-}
+// scratch: sb[T][K] doubles; si[T][K] ints followed by the T (low, high) count pairs
+size_t alias_value_doubles(const Dims &dm, int64_t T) { return (size_t)T * (size_t)dm.K; }
+size_t alias_stack_ints(const Dims &dm, int64_t T) { return alias_value_doubles(dm, T) + 2 * (size_t)T; }
 
 cudaError_t launch_alias_build(const Dims &dm, const float *alpha, const float *phiT, AliasSlot *table,
                                float *type_norm, double *bs_scratch, int32_t *stack_scratch,
-                               const int32_t *active, int32_t n_active, int sm_count, cudaStream_t st)
+                               const int32_t *active, int32_t n_active, int64_t T, int sm_count, cudaStream_t st)
 {
     if (n_active == 0) return cudaSuccess;
-    const int64_t T = alias_scratch_threads(dm, sm_count);
     int2 *counts = reinterpret_cast<int2 *>(stack_scratch + (size_t)T * dm.K);   // 8-byte aligned: T is a multiple of 128
     int per_sm = 1;
     cudaError_t e = kernel_config(reinterpret_cast<const void *>(alias_classify_kernel), ALIAS_CW * 32, 0, &per_sm);

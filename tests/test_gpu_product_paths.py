@@ -52,6 +52,32 @@ def test_sparse_slow_path_more_than_256_topics_per_document(oracle):
     s.close()
 
 
+def test_sparse_alias_tables_in_several_rounds(oracle, monkeypatch):
+    """kernels_sparse.cu launch_alias_build: when the active vocabulary exceeds the scratch slots the classify + pair
+    kernels run in rounds over slices of the active types (LDAGPU_ALIAS_SLOTS caps the slots; by default a round
+    covers 151 552 types).  The tables -- and so every sampled topic -- must not depend on the number of rounds
+    (reference: SpaliasUncollapsedParallelLDA.java:39-60 builds one table per type, independently)."""
+    K, V, D, mean_len = 1200, 900, 300, 120
+    off, tokens = make_corpus(D, V, mean_len, seed=8)
+    alpha, beta, seed = 50.0 / K, 0.01, 31
+    assert len(np.unique(tokens)) > 3 * 128, "several rounds of 128 slots"
+    monkeypatch.setenv("LDAGPU_ALIAS_SLOTS", "128")
+    s = _sampler("gpu_spalias", off, tokens, V, K, alpha, beta, seed)
+    monkeypatch.delenv("LDAGPU_ALIAS_SLOTS")
+    z0 = s.get_z_flat()
+    phi0 = s.getPhi().T.astype(np.float32).copy()
+    s.sample(2)
+    launches = s.getLastCallStats()[3]
+    st = oracle.sweeps("contract", oracle.SPALIAS, off, tokens, z0, V, K, np.full(K, alpha), beta, seed, 1, 2, phi0)
+    assert np.array_equal(s.get_z_flat(), st["z"])
+    assert np.array_equal(s.getTypeTopicMatrix(), st["n_wk"]) and np.array_equal(s.getTopicTotals(), st["n_k"])
+    # the same corpus with one round per build: the same chain, fewer launches
+    t = _sampler("gpu_spalias", off, tokens, V, K, alpha, beta, seed)
+    t.sample(2)
+    assert np.array_equal(t.get_z_flat(), st["z"]) and t.getLastCallStats()[3] < launches
+    s.close(); t.close()
+
+
 def test_set_z_eight_chunks_and_16_bit_upload():
     """ldagpu_set_z pipelines the upload in 8 chunks from N >= 8 Mi tokens on (engine.cu); the counts must equal a
     plain histogram.  ldagpu_set_z16 / ldagpu_sweep_get_z16 move the same indicators as uint16."""
