@@ -32,8 +32,11 @@ constexpr unsigned FULL = 0xffffffffu;
 //            the next one popped: it stays in registers), so each is a sequential stream: a lane keeps the next
 //            ALIAS_Q entries of either stack in registers and the warp tops all of them up together whenever one
 //            lane runs dry -- one memory round trip per ALIAS_Q steps instead of two dependent ones per step.
-//            (A deeper prefetch through per-lane rings in shared memory filled by cp.async removed the remaining
-//            load stalls but cost as many extra instructions as it saved cycles: 9.9 ms against 9.05.)
+//            (Two other structures were measured and lost: per-lane rings in shared memory filled by cp.async removed
+//            the remaining load stalls but cost as many extra instructions as they saved cycles, 9.9 ms against 9.05
+//            for the whole build; all lanes walking their low stacks in step, four entries per round from aligned
+//            vector loads one round ahead, left the rare per-lane events -- a new high, a high turned low -- running
+//            with one or two active lanes: 15 active threads per instruction on average, 14.4 ms.)
 // Round 1 ran both phases in one kernel, a warp classifying its 32 types one after the other: with ~45 000 active
 // types that is 9.5 warps per SM in long latency-bound loops (ncu: 12 long-scoreboard stalls per issue, 14 % issue
 // utilisation, 20.4 ms at K = 10 000).
