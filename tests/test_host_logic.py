@@ -270,3 +270,40 @@ int main() {
     assert r.returncode == 0, r.stderr[-2000:]
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout
+
+
+def test_library_carries_sm_100a_code_with_bulk_async_copies():
+    """The product library is native sm_100a code, not PTX for a JIT or another architecture: every embedded cubin is
+    sm_100a, the dense z-step kernels fetch their Phi^T rows with the TMA engine's bulk asynchronous copy (SASS UBLKCP,
+    completion on an mbarrier: SYNCS) and the Phi kernels' peer-memory exchange uses system-scope release / acquire."""
+    import shutil
+    import subprocess
+    from ldagroupedgibbssampler_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    so = _lib.library_path() if hasattr(_lib, "library_path") else os.path.join(ROOT, "ldagroupedgibbssampler_b200", "libldagpu.so")
+    elfs = subprocess.run([cuobjdump, "-lelf", so], capture_output=True, text=True, check=True).stdout
+    names = re.findall(r"ELF file\s+\d+:\s+(\S+)", elfs)
+    assert names and all(n.endswith(".sm_100a.cubin") for n in names), names
+    ptx = subprocess.run([cuobjdump, "-lptx", so], capture_output=True, text=True).stdout
+    assert "PTX file" not in ptx, "no PTX for a JIT: the kernels are compiled for sm_100a only"
+    sass = subprocess.run([cuobjdump, "-sass", so], capture_output=True, text=True, check=True).stdout
+    per_fn, cur = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            per_fn[cur] = set()
+        elif cur:
+            m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+            if m:
+                per_fn[cur].add(m.group(1))
+    z = {f: ops for f, ops in per_fn.items() if "z_kernelILi" in f}     # z_kernel<NT, PCGS>, not z_kernel_big
+    assert len(z) == 8, sorted(z)                              # NT in {1, 2, 4, 8} x {GGS, PCGS}
+    for f, ops in z.items():
+        assert "UBLKCP" in ops and "SYNCS" in ops, (f, "row fetch must be a bulk async copy on an mbarrier")
+    exchange = [ops for f, ops in per_fn.items() if "phi_draw_kernel" in f or "phi_normalise_kernel" in f]
+    assert exchange
+    all_sass = sass
+    assert ".STRONG.SYS" in all_sass, "peer-memory flags: system-scope release / acquire"
