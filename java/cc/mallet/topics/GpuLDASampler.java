@@ -16,6 +16,7 @@ import java.lang.invoke.MethodHandle;
 
 import cc.mallet.configuration.LDAConfiguration;
 import cc.mallet.types.Alphabet;
+import cc.mallet.types.Dirichlet;
 import cc.mallet.types.FeatureSequence;
 import cc.mallet.types.InstanceList;
 import cc.mallet.types.LabelSequence;
@@ -61,6 +62,11 @@ public class GpuLDASampler extends ModifiedSimpleLDA implements LDAGibbsSampler,
     private static final MethodHandle LOG_POSTERIOR = fn("ldagpu_log_posterior", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
     private static final MethodHandle ABORT = fn("ldagpu_abort", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     private static final MethodHandle SAMPLE_THETA = fn("ldagpu_sample_theta", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    // hyper-parameter optimisation hooks (ModifiedSimpleLDA.java:812-905, UncollapsedParallelLDA.java:891-894)
+    private static final MethodHandle GET_HISTOGRAMS = fn("ldagpu_get_count_histograms", FunctionDescriptor.of(JAVA_INT,
+            ADDRESS, JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
+    private static final MethodHandle SET_ALPHA = fn("ldagpu_set_alpha", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle SET_BETA = fn("ldagpu_set_beta", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_DOUBLE));
 
     private final Arena arena = Arena.ofShared();
     private MemorySegment handle = MemorySegment.NULL;
@@ -122,12 +128,22 @@ public class GpuLDASampler extends ModifiedSimpleLDA implements LDAGibbsSampler,
             docOffsets[d + 1] = docOffsets[d] + ((FeatureSequence) training.get(d).getData()).getLength();
         numTokens = (int) docOffsets[D];
         int[] tokens = new int[numTokens];
+        int longestDoc = 0;
         for (int d = 0; d < D; d++) {
             FeatureSequence fs = (FeatureSequence) training.get(d).getData();
             // the backing array may be longer than getLength() (TestInitialization.java:346-349)
             System.arraycopy(fs.getFeatures(), 0, tokens, (int) docOffsets[d], fs.getLength());
             data.add(new TopicAssignment(training.get(d), new LabelSequence(topicAlphabet, new int[fs.getLength()])));
+            longestDoc = Math.max(longestDoc, fs.getLength());
         }
+        // sufficient statistics of the hyper-parameter optimisation that do not change with z
+        // (UncollapsedParallelLDA.java:408-431): histogram of document lengths, largest corpus frequency of a type
+        docLengthCounts = new int[longestDoc + 1];
+        for (int d = 0; d < D; d++) docLengthCounts[(int) (docOffsets[d + 1] - docOffsets[d])]++;
+        int[] typeTotals = new int[numTypes];
+        for (int t : tokens) typeTotals[t]++;
+        maxTypeCount = 0;
+        for (int c : typeTotals) maxTypeCount = Math.max(maxTypeCount, c);
         try {
             MemorySegment out = arena.allocate(ADDRESS);
             int[] devices = gpuDevices();
@@ -182,6 +198,8 @@ public class GpuLDASampler extends ModifiedSimpleLDA implements LDAGibbsSampler,
             try { ck((int) SET_MEAN_SCHEDULE.invokeExact(handle, burn, config.getPhiMeanThin(1))); }
             catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new IllegalStateException(t); }
         }
+        // UPL:214,891-894: alpha and beta are re-estimated every hyperparam_optim_interval sweeps (off by default)
+        int hyperInterval = config.getHyperparamOptimInterval(LDAConfiguration.HYPERPARAM_OPTIM_INTERVAL_DEFAULT);
         int done = 0;
         // UPL:577,926-928: stop when zSamplingTimeCum + phiSamplingTimeCum reaches exec_time (default 10 s,
         // LDAConfiguration.java:35), counted from the start of THIS call; the abort flag is checked as often (UPL:645)
@@ -192,11 +210,17 @@ public class GpuLDASampler extends ModifiedSimpleLDA implements LDAGibbsSampler,
             while (done < iterations && !abort) {
                 int step = Math.min(Math.min(interval, SWEEPS_PER_CALL), iterations - done);
                 if (config.computeLikelihood()) step = Math.min(step, interval - done % interval);
+                if (hyperInterval > 1) step = Math.min(step, hyperInterval - done % hyperInterval);
                 preIteration();
                 ck((int) SWEEP.invokeExact(handle, step, n));
                 done += n.get(JAVA_INT, 0);
                 currentIteration = done;
                 if (config.computeLikelihood() && done % interval == 0) loglikelihood.add(modelLogLikelihood());
+                if (hyperInterval > 1 && done % hyperInterval == 0) {
+                    pullZ();              // tokensPerTopic for the topic-size histogram
+                    optimizeAlpha();
+                    optimizeBeta();
+                }
                 postIteration();
                 if (n.get(JAVA_INT, 0) < step) break;
                 if (maxExecTimeMillis > 0 && samplingMillis(a) - t0 >= maxExecTimeMillis) break;
@@ -307,6 +331,42 @@ public class GpuLDASampler extends ModifiedSimpleLDA implements LDAGibbsSampler,
             MemorySegment v = a.allocate(JAVA_DOUBLE);
             ck((int) LOG_POSTERIOR.invokeExact(handle, v));
             return v.get(JAVA_DOUBLE, 0);
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new IllegalStateException(t); }
+    }
+
+    /** ModifiedSimpleLDA.java:812-858, symmetric alpha (the GPU path keeps alpha symmetric).  The reference fills
+     *  documentTopicHistogram inside its z-step (UPL:1382-1401); here the library counts the (document, topic)
+     *  pairs with n_dk = c from the current z, and MALLET's fixed point runs on the host as before. */
+    @Override
+    public void optimizeAlpha() {
+        int bins = docLengthCounts.length;
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment dh = a.allocate(JAVA_LONG, bins);
+            ck((int) GET_HISTOGRAMS.invokeExact(handle, bins, dh, 0, MemorySegment.NULL));
+            int[] hist = new int[bins];
+            for (int c = 0; c < bins; c++) hist[c] = (int) dh.getAtIndex(JAVA_LONG, c);
+            alphaSum = Dirichlet.learnSymmetricConcentration(hist, docLengthCounts, numTopics, alphaSum);
+            java.util.Arrays.fill(alpha, alphaSum / numTopics);
+            ck((int) SET_ALPHA.invokeExact(handle, a.allocateFrom(JAVA_DOUBLE, alpha)));
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new IllegalStateException(t); }
+    }
+
+    /** ModifiedSimpleLDA.java:860-905: the histogram of n_wk comes from the library, the topic sizes from tokensPerTopic */
+    @Override
+    public void optimizeBeta() {
+        int bins = maxTypeCount + 1;
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment th = a.allocate(JAVA_LONG, bins);
+            ck((int) GET_HISTOGRAMS.invokeExact(handle, 0, MemorySegment.NULL, bins, th));
+            int[] countHistogram = new int[bins];
+            for (int c = 0; c < bins; c++) countHistogram[c] = (int) Math.min(th.getAtIndex(JAVA_LONG, c), Integer.MAX_VALUE);
+            int maxTopicSize = 0;
+            for (int k = 0; k < numTopics; k++) maxTopicSize = Math.max(maxTopicSize, tokensPerTopic[k]);
+            int[] topicSizeHistogram = new int[maxTopicSize + 1];
+            for (int k = 0; k < numTopics; k++) topicSizeHistogram[tokensPerTopic[k]]++;
+            betaSum = Dirichlet.learnSymmetricConcentration(countHistogram, topicSizeHistogram, numTypes, betaSum);
+            beta = betaSum / numTypes;
+            ck((int) SET_BETA.invokeExact(handle, beta));
         } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new IllegalStateException(t); }
     }
 

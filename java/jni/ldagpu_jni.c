@@ -27,6 +27,9 @@
  *       static native double logLikelihood(long h);
  *       static native double logPosterior(long h);
  *       static native void   abort(long h);
+ *       static native void   getCountHistograms(long h, long[] docTopicHist, long[] typeTopicHist);   // either may be empty
+ *       static native void   setAlpha(long h, double[] alpha);           // optimizeAlpha / optimizeBeta (MSL:812-905)
+ *       static native void   setBeta(long h, double beta);
  *   }
  * Every failure is rethrown as IllegalStateException with ldagpu_last_error's message, which is what the
  * reference's own samplers throw on an invariant break (UncollapsedParallelLDA.java:475-481,1828-1830).
@@ -158,4 +161,34 @@ JNIEXPORT void JNICALL CLS(abort)(JNIEnv *env, jclass c, jlong h)
 {
     (void)env; (void)c;
     ldagpu_abort((ldagpu_handle)(intptr_t)h);
+}
+
+/* hyper-parameter optimisation hooks (ModifiedSimpleLDA.java:812-905): MALLET's fixed point stays in Java */
+JNIEXPORT void JNICALL CLS(getCountHistograms)(JNIEnv *env, jclass c, jlong h, jlongArray docTopicHist,
+                                               jlongArray typeTopicHist)
+{
+    (void)c;
+    jsize nd = (*env)->GetArrayLength(env, docTopicHist), nt = (*env)->GetArrayLength(env, typeTopicHist);
+    jlong *d = (*env)->GetLongArrayElements(env, docTopicHist, NULL);
+    jlong *t = (*env)->GetLongArrayElements(env, typeTopicHist, NULL);
+    int rc = ldagpu_get_count_histograms((ldagpu_handle)(intptr_t)h, (int32_t)nd, nd ? (int64_t *)d : NULL,
+                                         (int32_t)nt, nt ? (int64_t *)t : NULL);
+    (*env)->ReleaseLongArrayElements(env, docTopicHist, d, 0);
+    (*env)->ReleaseLongArrayElements(env, typeTopicHist, t, 0);
+    if (rc) throw_last(env, (ldagpu_handle)(intptr_t)h);
+}
+
+JNIEXPORT void JNICALL CLS(setAlpha)(JNIEnv *env, jclass c, jlong h, jdoubleArray alpha)
+{
+    (void)c;
+    jdouble *a = (*env)->GetDoubleArrayElements(env, alpha, NULL);
+    int rc = ldagpu_set_alpha((ldagpu_handle)(intptr_t)h, (const double *)a);
+    (*env)->ReleaseDoubleArrayElements(env, alpha, a, JNI_ABORT);
+    if (rc) throw_last(env, (ldagpu_handle)(intptr_t)h);
+}
+
+JNIEXPORT void JNICALL CLS(setBeta)(JNIEnv *env, jclass c, jlong h, jdouble beta)
+{
+    (void)c;
+    if (ldagpu_set_beta((ldagpu_handle)(intptr_t)h, beta)) throw_last(env, (ldagpu_handle)(intptr_t)h);
 }
