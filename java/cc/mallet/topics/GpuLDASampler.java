@@ -10,6 +10,7 @@ package cc.mallet.topics;
 //     ~60-line JNI stub; the C signatures are identical.
 // Factory wiring: two `case` labels in topics/tui/ParallelLDA.java:401-490, see INTEGRATION.md.
 
+import java.io.File;
 import java.io.IOException;
 import java.lang.foreign.*;
 import java.lang.invoke.MethodHandle;
@@ -20,11 +21,14 @@ import cc.mallet.types.Dirichlet;
 import cc.mallet.types.FeatureSequence;
 import cc.mallet.types.InstanceList;
 import cc.mallet.types.LabelSequence;
+import cc.mallet.util.LDAUtils;
+import cc.mallet.util.LoggingUtils;
 
 import static java.lang.foreign.ValueLayout.*;
 
 public class GpuLDASampler extends ModifiedSimpleLDA implements LDAGibbsSampler, LDASamplerWithPhi {
     private static final long serialVersionUID = 1L;
+    private static final java.util.logging.Logger LOG = java.util.logging.Logger.getLogger(GpuLDASampler.class.getName());
 
     // ---- C ABI --------------------------------------------------------------------------------
     private static final Linker LINKER = Linker.nativeLinker();
@@ -187,8 +191,8 @@ public class GpuLDASampler extends ModifiedSimpleLDA implements LDAGibbsSampler,
         }
     }
 
-    /** UncollapsedParallelLDA.java:552-943.  Diagnostics (log-posterior / log-likelihood files,
-     *  UPL:707-853) stay in Java and read the scalars from the library. */
+    /** UncollapsedParallelLDA.java:552-943.  Diagnostics (log-posterior / log-likelihood files, Phi / Theta dumps,
+     *  UPL:707-853) stay in Java -- written by the reference's LDAUtils -- and read their inputs from the library. */
     @Override
     public void sample(int iterations) throws IOException {
         preSample();
@@ -198,6 +202,13 @@ public class GpuLDASampler extends ModifiedSimpleLDA implements LDAGibbsSampler,
             try { ck((int) SET_MEAN_SCHEDULE.invokeExact(handle, burn, config.getPhiMeanThin(1))); }
             catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new IllegalStateException(t); }
         }
+        // UPL:555-581: the diagnostic block's settings and output directories
+        int startDiagnostic = config.getStartDiagnostic(LDAConfiguration.START_DIAG_DEFAULT);
+        int[] printFirstNDocs = config.getPrintNDocsInterval();
+        int nDocs = config.getPrintNDocs();
+        boolean savePhi = config.getSavePhi();
+        String loggingPath = config.getLoggingUtil().getLogDir().getAbsolutePath();
+        File asciiOutput = LoggingUtils.checkCreateAndCreateDir(loggingPath + "/ascii");
         // UPL:214,891-894: alpha and beta are re-estimated every hyperparam_optim_interval sweeps (off by default)
         int hyperInterval = config.getHyperparamOptimInterval(LDAConfiguration.HYPERPARAM_OPTIM_INTERVAL_DEFAULT);
         int done = 0;
@@ -211,11 +222,16 @@ public class GpuLDASampler extends ModifiedSimpleLDA implements LDAGibbsSampler,
                 int step = Math.min(Math.min(interval, SWEEPS_PER_CALL), iterations - done);
                 if (config.computeLikelihood()) step = Math.min(step, interval - done % interval);
                 if (hyperInterval > 1) step = Math.min(step, hyperInterval - done % hyperInterval);
+                // the diagnostic block runs after EVERY sweep from start_diagnostic on (UPL:706-823): one sweep per call
+                // there, and the last call before it must stop right at start_diagnostic - 1
+                if (startDiagnostic > 0) step = done + 1 >= startDiagnostic ? 1 : Math.min(step, startDiagnostic - 1 - done);
                 preIteration();
                 ck((int) SWEEP.invokeExact(handle, step, n));
                 done += n.get(JAVA_INT, 0);
                 currentIteration = done;
                 if (config.computeLikelihood() && done % interval == 0) loglikelihood.add(modelLogLikelihood());
+                if (startDiagnostic > 0 && done >= startDiagnostic && n.get(JAVA_INT, 0) > 0)
+                    diagnostics(done, printFirstNDocs, nDocs, savePhi, asciiOutput, loggingPath);
                 if (hyperInterval > 1 && done % hyperInterval == 0) {
                     pullZ();              // tokensPerTopic for the topic-size histogram
                     optimizeAlpha();
@@ -225,13 +241,46 @@ public class GpuLDASampler extends ModifiedSimpleLDA implements LDAGibbsSampler,
                 if (n.get(JAVA_INT, 0) < step) break;
                 if (maxExecTimeMillis > 0 && samplingMillis(a) - t0 >= maxExecTimeMillis) break;
             }
-        } catch (RuntimeException e) {
+        } catch (RuntimeException | IOException e) {
             throw e;
         } catch (Throwable t) {
             throw new IllegalStateException(t);
         }
         pullZ();
         postSample();
+    }
+
+    /** The diagnostic block of UPL:706-823, fed from the library: `Theta_DxK_<n>_<K>_<iter>.csv` for the first n
+     *  documents when the iteration lies in print_ndocs_interval, `Phi_KxV_<K>_<V>_<iter>.csv` when save_phi is set,
+     *  and one line of log-posterior.txt -- written by the reference's own LDAUtils (util/LDAUtils.java:955-968,
+     *  1223-1254), so formats are the reference's by construction. */
+    private void diagnostics(int iteration, int[] printFirstNDocs, int nDocs, boolean savePhi, File asciiOutput,
+                             String loggingPath) throws IOException {
+        if (printFirstNDocs.length > 1 && LDAUtils.inRangeInterval(iteration, printFirstNDocs)) {
+            // GGS: the sweep's own theta (UPL:716-720); the other schemes: theta ~ Dir(n_d + alpha) from the current z
+            // (UPL:710-714) -- the draw is keyed by (sweep, document, topic), so computeLogPosterior() below sees the same one
+            double[][] theta = diagnosticTheta();
+            double[][] head = java.util.Arrays.copyOf(theta, Math.min(nDocs, theta.length));
+            LDAUtils.writeASCIIDoubleMatrix(head, String.format(asciiOutput.getAbsolutePath() + "/Theta_DxK_" + nDocs + "_"
+                    + numTopics + "_%05d.csv", iteration), ",");
+        }
+        if (savePhi)
+            LDAUtils.writeASCIIDoubleMatrix(getPhi(), String.format(asciiOutput.getAbsolutePath() + "/Phi_KxV_" + numTopics
+                    + "_" + numTypes + "_%05d.csv", iteration), ",");
+        LDAUtils.logPosteriorToFile(computeLogPosterior(), iteration, loggingPath, LOG);
+    }
+
+    /** double[D][K]: GGS thetaMatrix of the last sweep, or the diagnostic theta of the other schemes */
+    public double[][] diagnosticTheta() {
+        int D = data.size();
+        double[][] out = new double[D][numTopics];
+        try (Arena a = Arena.ofConfined()) {
+            if (scheme != 0) ck((int) SAMPLE_THETA.invokeExact(handle));
+            MemorySegment m = a.allocate(JAVA_DOUBLE, (long) D * numTopics);
+            ck((int) GET_THETA.invokeExact(handle, m));
+            for (int d = 0; d < D; d++) MemorySegment.copy(m, JAVA_DOUBLE, (long) d * numTopics * 8, out[d], 0, numTopics);
+        } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new IllegalStateException(t); }
+        return out;
     }
 
     /** z + count merge + Phi + exchange time so far, in ms (the reference's zSamplingTimeCum + phiSamplingTimeCum) */
